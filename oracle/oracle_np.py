@@ -1,0 +1,541 @@
+"""CPU ORACLE (numpy) for the batched BlueROV2 / legacy-AUV env-step path.
+
+TEST INFRASTRUCTURE ONLY.  This file restates the reference's algorithm in
+numpy so that the CUDA path can be checked on machines where /root/reference
+does not exist.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU-baseline legs may import it; the product package never does
+(the product fails loudly when its CUDA library is missing).
+
+Parity pin: the reference ships no tests and no golden vectors for this path
+(the single in-repo vector, example_temp.py:19-28, is
+checked in tests/test_oracle_golden.py).  The oracle is therefore pinned
+against outputs of the UNMODIFIED reference executed in the build container:
+``tests/golden/golden_*.npz`` written by ``tests/golden/gen_golden_*.py``.
+
+Every function is vectorised over a leading batch axis ``N`` (array-of-structs
+``[N, k]`` - the natural numpy layout; the CUDA library uses ``[k][N]``).
+Reference citations are ``file:line`` relative to the reference root, with
+``6DoF.py`` = dynamicsModel_BlueROV2_Heavy_6DoF.py, ``3DoF.py`` =
+dynamicsModel_BlueROV2_Heavy_3DoF.py, ``legacy/`` =
+tag_00_Dec2023_simpleControlTurbulence/.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+TWO_PI = 2.0 * np.pi
+
+
+# ==========================================================================
+# resources.py helpers
+# ==========================================================================
+def compute_thrust_allocation(positions, normals, x0=None):
+    """resources.py:19-35 - A[:, i] = [n_i ; (r_i - x0) x n_i], Ainv = pinv(A)."""
+    positions = np.asarray(positions, dtype=float)
+    normals = np.asarray(normals, dtype=float)
+    if x0 is None:
+        x0 = np.zeros(3)
+    A = np.zeros((6, positions.shape[0]))
+    for i in range(positions.shape[0]):
+        A[:3, i] = normals[i]
+        A[3:, i] = np.cross(positions[i] - x0, normals[i])
+    return A, np.linalg.pinv(A)
+
+
+def angle_error(psi_d, psi):
+    """resources.py:75-95 (== legacy/resources.py:26-46).  Python-modulo
+    semantics; returns -0.0 for equal angles and -pi for a == b == pi."""
+    psi_d = np.asarray(psi_d, dtype=float)
+    psi = np.asarray(psi, dtype=float)
+    a = np.mod(psi_d - psi, TWO_PI)
+    b = np.mod(psi - psi_d, TWO_PI)
+    return np.where(a < b, a, -b)
+
+
+def coordinate_transform6(phi, theta, psi):
+    """resources.py:115-141 -> [N, 6, 6].  Bug-compatible: J1[0,2] carries
+    sin(phi) in its second term (Fossen has cos(phi)); cos(theta) in J2's
+    denominators is clamped away from zero as at resources.py:116-120."""
+    phi, theta, psi = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (phi, theta, psi))
+    sph, cph = np.sin(phi), np.cos(phi)
+    sth, cth = np.sin(theta), np.cos(theta)
+    sps, cps = np.sin(psi), np.cos(psi)
+    den = np.where(np.abs(cth) < 1e-12, 1e-6, np.where(np.abs(cth) < 1e-6, 1e-6 * np.sign(cth), cth))
+    J = np.zeros(phi.shape + (6, 6))
+    J[..., 0, 0] = cps * cth
+    J[..., 0, 1] = -sps * cph + cps * sth * sph
+    J[..., 0, 2] = sps * sph + cps * sth * sph
+    J[..., 1, 0] = sps * cth
+    J[..., 1, 1] = cps * cph + sps * sth * sph
+    J[..., 1, 2] = -cps * sph + sps * sth * cph
+    J[..., 2, 0] = -sth
+    J[..., 2, 1] = cth * sph
+    J[..., 2, 2] = cth * cph
+    J[..., 3, 3] = 1.0
+    J[..., 3, 4] = sph * sth / den
+    J[..., 3, 5] = cph * sth / den
+    J[..., 4, 4] = cph
+    J[..., 4, 5] = -sph
+    J[..., 5, 4] = sph / den
+    J[..., 5, 5] = cph / den
+    return J
+
+
+def coordinate_transform3(psi):
+    """resources.py:108-113 -> [N, 3, 3] planar rotation."""
+    psi = np.atleast_1d(np.asarray(psi, dtype=float))
+    J = np.zeros(psi.shape + (3, 3))
+    J[..., 0, 0] = np.cos(psi)
+    J[..., 0, 1] = -np.sin(psi)
+    J[..., 1, 0] = np.sin(psi)
+    J[..., 1, 1] = np.cos(psi)
+    J[..., 2, 2] = 1.0
+    return J
+
+
+# ==========================================================================
+# 6DoF model
+# ==========================================================================
+@dataclass
+class Rov6Params:
+    """6DoF.py:83-218.  Attribute names are the reference's."""
+    rho_f: float = 1000.
+    m: float = 11.4
+    Length: float = 0.457
+    Width: float = 0.338
+    CB: np.ndarray = field(default_factory=lambda: np.array([0., 0., 0.]))
+    CG: np.ndarray = field(default_factory=lambda: np.array([0., 0., 0.05]))
+    I: np.ndarray = field(default_factory=lambda: np.diag([0.16, 0.16, 0.16]))
+    Xudot: float = -5.5
+    Yvdot: float = -12.7
+    Zwdot: float = -14.57
+    Kpdot: float = -0.12
+    Mqdot: float = -0.12
+    Nrdot: float = -0.12
+    Yrdot: float = 0.
+    Zvdot: float = 0.
+    Nvdot: float = 0.
+    Xuu: float = -18.18
+    Yvv: float = -21.66
+    Zww: float = -36.99
+    Kpp: float = -1.55
+    Mqq: float = -1.55
+    Nrr: float = -1.55
+    Yrr: float = 0.
+    Ypp: float = 0.
+    Zqq: float = 0.
+    Kvv: float = 0.
+    Krr: float = 0.
+    Mww: float = -1.55
+    Nvv: float = 0.
+    Npp: float = 0.
+    Xu: float = -4.03
+    Yv: float = -6.22
+    Zw: float = -5.18
+    Kp: float = -0.07
+    Mq: float = -0.07
+    Nr: float = -0.07
+    Yr: float = 0.
+    Yp: float = 0.
+    Zq: float = 0.
+    Kv: float = 0.
+    Kr: float = 0.
+    Mw: float = 0.
+    Nv: float = 0.
+    Np: float = 0.
+    D_thruster: float = 0.1
+    alphaThruster: float = 33. / 180. * np.pi
+    l_x: float = 0.1475
+    l_y: float = 0.101
+    l_z: float = 0.068
+    l_x_v: float = 0.120
+    l_y_v: float = 0.22
+    l_z_v: float = 0.0
+
+    def __post_init__(self):
+        self.dispVol = self.m / self.rho_f
+        self.Kt_thruster = 40. / (1000. * (3500. / 60.) ** 2. * self.D_thruster ** 4.)
+        a = self.alphaThruster
+        self.thrusterPositions = np.array([
+            [self.l_x, self.l_y, self.l_z], [self.l_x, -self.l_y, self.l_z],
+            [-self.l_x, self.l_y, self.l_z], [-self.l_x, -self.l_y, self.l_z],
+            [self.l_x_v, self.l_y_v, self.l_z_v], [self.l_x_v, -self.l_y_v, self.l_z_v],
+            [-self.l_x_v, self.l_y_v, self.l_z_v], [-self.l_x_v, -self.l_y_v, self.l_z_v]])
+        self.thrusterNormals = np.array([
+            [np.cos(a), -np.sin(a), 0.], [np.cos(a), np.sin(a), 0.],
+            [-np.cos(a), -np.sin(a), 0.], [-np.cos(a), np.sin(a), 0.],
+            [0., 0., -1.], [0., 0., 1.], [0., 0., 1.], [0., 0., -1.]])
+        self.A, self.Ainv = compute_thrust_allocation(self.thrusterPositions, self.thrusterNormals)
+
+    # 6DoF.py:286-299.  NB Ma[2,2] uses Zvdot (= 0), not Zwdot.
+    def mass_matrix(self):
+        m, (xg, yg, zg) = self.m, self.CG
+        Mrb = np.array([
+            [m, 0., 0., 0., m * zg, -m * yg],
+            [0., m, 0., -m * zg, 0., m * xg],
+            [0., 0., m, m * yg, -m * xg, 0.],
+            [0., -m * zg, m * yg, 0., 0., 0.],
+            [m * zg, 0., -m * xg, 0., 0., 0.],
+            [-m * yg, m * xg, 0., 0., 0., 0.]])
+        Mrb[3:, 3:] = self.I
+        Ma = -1. * np.diag([self.Xudot, self.Yvdot, self.Zvdot, self.Kpdot, self.Mqdot, self.Nrdot])
+        return Mrb + Ma
+
+
+PID6_WINDUP = np.array([2., 2., 2., 90. / 180. * np.pi, 90. / 180. * np.pi, 90. / 180. * np.pi])
+PID6_MAX = np.array([50., 50., 50., 1., 1., 2.])
+PID6_KP = np.array([25., 25., 25., 10., 10., 1.])
+PID6_KI = np.array([2., 2., 2., 0.1, 0.1, 0.2])
+PID6_KD = np.array([20., 20., 20., 5., 5., 0.65])
+
+
+def pid6_new_state(n):
+    """6DoF.py:37-41: eOld=None, eInt=0, tOld=0."""
+    return {"eOld": np.zeros((n, 6)), "has_old": np.zeros(n, dtype=bool),
+            "eInt": np.zeros((n, 6)), "tOld": np.zeros(n)}
+
+
+def pid6_control(ctrl, set_point, pose, t):
+    """6DoF.py:43-73 - mutates ``ctrl`` exactly like the reference mutates the
+    controller on EVERY call.  Roll/pitch errors are raw differences, yaw is
+    wrapped; dedt divides by max(1e-9, t - tOld)."""
+    set_point = np.asarray(set_point, dtype=float)
+    pose = np.asarray(pose, dtype=float)
+    t = np.broadcast_to(np.asarray(t, dtype=float), pose.shape[:1])
+    e = np.empty_like(pose)
+    e[:, 0:3] = set_point[:, 0:3] - pose[:, 0:3]
+    e[:, 3] = set_point[:, 3] - pose[:, 3]
+    e[:, 4] = set_point[:, 4] - pose[:, 4]
+    e[:, 5] = angle_error(set_point[:, 5], pose[:, 5])
+    e_old = np.where(ctrl["has_old"][:, None], ctrl["eOld"], e)
+    dtc = t - ctrl["tOld"]
+    dedt = (e - e_old) / np.maximum(1e-9, dtc)[:, None]
+    e_int = ctrl["eInt"] + 0.5 * (e_old + e) * dtc[:, None]
+    e_int = np.where(np.abs(e) > PID6_WINDUP, 0., e_int)
+    u = PID6_KP * e + PID6_KD * dedt + PID6_KI * e_int
+    u = np.maximum(-PID6_MAX, np.minimum(PID6_MAX, u))
+    ctrl["eOld"] = e
+    ctrl["has_old"] = np.ones_like(ctrl["has_old"])
+    ctrl["eInt"] = e_int
+    ctrl["tOld"] = t.copy()
+    return u
+
+
+def body_axes(angles):
+    """6DoF.py:238-242: rows of R^T for the intrinsic-XYZ rotation
+    R = Rx(phi) Ry(theta) Rz(psi) (closed form of scipy's
+    Rotation.from_euler('XYZ')) -> iHat, jHat, kHat, each [N, 3]."""
+    phi, th, psi = angles[:, 0], angles[:, 1], angles[:, 2]
+    sph, cph, sth, cth, sps, cps = np.sin(phi), np.cos(phi), np.sin(th), np.cos(th), np.sin(psi), np.cos(psi)
+    i_hat = np.stack([cth * cps, cph * sps + sph * sth * cps, sph * sps - cph * sth * cps], axis=1)
+    j_hat = np.stack([-cth * sps, cph * cps - sph * sth * sps, sph * cps + cph * sth * sps], axis=1)
+    k_hat = np.stack([sth, -sph * cth, cph * cth], axis=1)
+    return i_hat, j_hat, k_hat
+
+
+def global_to_vehicle(axes, v):
+    """6DoF.py:244-248."""
+    return np.stack([np.sum(v * axes[0], axis=1), np.sum(v * axes[1], axis=1), np.sum(v * axes[2], axis=1)], axis=1)
+
+
+def allocate_thrust6(p, axes, gcf):
+    """6DoF.py:220-231: earth-frame forces AND moments are rotated like
+    vectors into the body frame, then rpm = sign(c) sqrt(|c|/(rho D^4 Kt)) 60."""
+    body = np.concatenate([global_to_vehicle(axes, gcf[:, :3]), global_to_vehicle(axes, gcf[:, 3:])], axis=1)
+    cv = body @ p.Ainv.T
+    return np.sign(cv) * np.sqrt(np.abs(cv) / (p.rho_f * p.D_thruster ** 4. * p.Kt_thruster)) * 60.
+
+
+def limit_rpm(rpm):
+    """6DoF.py:271-275: saturate at +-3500, zero inside the 300 rpm deadband."""
+    r = np.maximum(-3500., np.minimum(3500., rpm))
+    return np.where(np.abs(r) < 300, 0., r)
+
+
+def thruster_force6(p, rpm):
+    """6DoF.py:233-236."""
+    return p.rho_f * (rpm / 60.) ** 2. * np.sign(rpm) * p.D_thruster ** 4. * p.Kt_thruster
+
+
+def force_components6(p, angles, vel, rpm):
+    """6DoF.py:253-404 -> (-Crb v, -Ca v, -D v, G, H), each [N, 6]."""
+    m = p.m
+    xg, yg, zg = p.CG
+    Im = p.I
+    phi, theta = angles[:, 0], angles[:, 1]
+    u, v, w, pp, q, r = (vel[:, i] for i in range(6))
+
+    H = thruster_force6(p, limit_rpm(rpm)) @ p.A.T  # 6DoF.py:278-282
+
+    # Crb v, 6DoF.py:303-332
+    a1 = m * (yg * q + zg * r); a2 = m * (xg * q - w); a3 = m * (xg * r + v)
+    b1 = m * (yg * pp + w); b2 = m * (zg * r + xg * pp); b3 = m * (yg * r - u)
+    c1 = m * (zg * pp - v); c2 = m * (zg * q + u); c3 = m * (xg * pp + yg * q)
+    i1 = -Im[1, 2] * q - Im[0, 2] * pp + Im[2, 2] * r
+    i2 = Im[1, 2] * r + Im[0, 1] * pp - Im[1, 1] * q
+    i3 = -Im[0, 2] * r - Im[0, 1] * q + Im[0, 0] * pp
+    crb = np.stack([
+        a1 * pp - a2 * q - a3 * r,
+        -b1 * pp + b2 * q - b3 * r,
+        -c1 * pp - c2 * q + c3 * r,
+        -a1 * u + b1 * v + c1 * w + i1 * q + i2 * r,
+        a2 * u - b2 * v + c2 * w - i1 * pp + i3 * r,
+        a3 * u + b3 * v - c3 * w - i2 * pp - i3 * q], axis=1)
+
+    # Ca v, 6DoF.py:334-341 (uses Zwdot although Ma uses Zvdot)
+    Xd, Yd, Zd, Kd, Md, Nd = p.Xudot, p.Yvdot, p.Zwdot, p.Kpdot, p.Mqdot, p.Nrdot
+    ca = np.stack([
+        -Zd * w * q + Yd * v * r,
+        Zd * w * pp - Xd * u * r,
+        -Yd * v * pp + Xd * u * q,
+        -Zd * w * v + Yd * v * w - Nd * r * q + Md * q * r,
+        Zd * w * u - Xd * u * w + Nd * r * pp - Kd * pp * r,
+        -Yd * v * u + Xd * u * v - Md * q * pp + Kd * pp * q], axis=1)
+
+    # -D v, 6DoF.py:345-370 (D = -(Dl + Dq|v|), so -D v = +(coef) v)
+    au, av, aw, ap, aq, ar = (np.abs(x) for x in (u, v, w, pp, q, r))
+    mdv = np.stack([
+        (p.Xu + p.Xuu * au) * u,
+        (p.Yv + p.Yvv * av) * v + (p.Yp + p.Ypp * ap) * pp + (p.Yr + p.Yrr * ar) * r,
+        (p.Zw + p.Zww * aw) * w + (p.Zq + p.Zqq * aq) * q,
+        (p.Kv + p.Kvv * av) * v + (p.Kp + p.Kpp * ap) * pp + (p.Kr + p.Krr * ar) * r,
+        (p.Mw + p.Mww * aw) * w + (p.Mq + p.Mqq * aq) * q,
+        (p.Nv + p.Nvv * av) * v + (p.Np + p.Npp * ap) * pp + (p.Nr + p.Nrr * ar) * r], axis=1)
+
+    # G, 6DoF.py:374-388
+    W = p.m * 9.81
+    B = p.dispVol * p.rho_f * 9.81
+    xb, yb, zb = p.CB
+    sth, cth, sph, cph = np.sin(theta), np.cos(theta), np.sin(phi), np.cos(phi)
+    G = np.stack([
+        (W - B) * sth,
+        -(W - B) * cth * sph,
+        -(W - B) * cth * cph,
+        -(yg * W - yb * B) * cth * cph + (zg * W - zb * B) * cth * sph,
+        (zg * W - zb * B) * sth + (xg * W - xb * B) * cth * cph,
+        -(xg * W - xb * B) * cth * sph - (yg * W - yb * B) * sth], axis=1)
+    return -crb, -ca, mdv, G, H
+
+
+def rhs6(p, angles, vel, rpm):
+    """6DoF.py:396 with velCurrent = 0 and E = 0."""
+    mcrb, mca, mdv, G, H = force_components6(p, angles, vel, rpm)
+    return mcrb + mca + mdv - G + H
+
+
+def _eta_dot6(angles, vel):
+    J = coordinate_transform6(angles[:, 0], angles[:, 1], angles[:, 2])
+    return np.einsum("nij,nj->ni", J, vel)
+
+
+def derivs6_rpm(p, state, rpm):
+    """6DoF.py:424-442 with the thruster rpm given directly."""
+    state = np.atleast_2d(np.asarray(state, dtype=float))
+    rpm = np.atleast_2d(np.asarray(rpm, dtype=float))
+    angles, vel = state[:, 3:6], state[:, 6:12]
+    acc = np.linalg.solve(p.mass_matrix(), rhs6(p, angles, vel, rpm).T).T
+    return np.concatenate([_eta_dot6(angles, vel), acc], axis=1)
+
+
+def derivs6_force(p, state, gcf, return_cv=False):
+    """6DoF.py:406-442 with a stateless controller returning ``gcf``."""
+    state = np.atleast_2d(np.asarray(state, dtype=float))
+    gcf = np.atleast_2d(np.asarray(gcf, dtype=float))
+    cv = allocate_thrust6(p, body_axes(state[:, 3:6]), gcf)
+    d = derivs6_rpm(p, state, cv)
+    return (d, cv) if return_cv else d
+
+
+def derivs6_pid(p, t, state, ctrl, set_point, return_aux=False):
+    """6DoF.py:406-442 with the reference's stateful PID (mutates ``ctrl``)."""
+    state = np.atleast_2d(np.asarray(state, dtype=float))
+    gcf = pid6_control(ctrl, set_point, state[:, 0:6], t)
+    d, cv = derivs6_force(p, state, gcf, return_cv=True)
+    return (d, gcf, cv) if return_aux else d
+
+
+# ==========================================================================
+# fixed-step RK4 (the integrator both sides of every parity test use)
+# ==========================================================================
+def rk4_substep(f, t, y, h):
+    k1 = f(t, y)
+    k2 = f(t + 0.5 * h, y + 0.5 * h * k1)
+    k3 = f(t + 0.5 * h, y + 0.5 * h * k2)
+    k4 = f(t + h, y + h * k3)
+    return y + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+
+
+def rk4_advance(f, t0, y, dt, n_sub):
+    h = dt / n_sub
+    for j in range(n_sub):
+        y = rk4_substep(f, t0 + j * h, y, h)
+    return y
+
+
+# ==========================================================================
+# counter-based RNG used for auto-reset (Philox4x32-10; new in the build -
+# the reference draws from the unseeded global numpy RNG, 6DoF.py:497-498)
+# ==========================================================================
+_PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PH_W0, _PH_W1 = 0x9E3779B9, 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32(counter, key):
+    """counter: [N, 4] uint32, key: (k0, k1) -> [N, 4] uint32."""
+    c = [np.asarray(counter[:, i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _PH_M0 * c[0]
+        p1 = _PH_M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        c = [(hi1 ^ c[1] ^ np.uint64(k0)) & _MASK32, lo1, (hi0 ^ c[3] ^ np.uint64(k1)) & _MASK32, lo0]
+        k0 = (k0 + _PH_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PH_W1) & 0xFFFFFFFF
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def philox_uniform(seed, env_id, episode, n_values, stream=0):
+    """n_values uniforms in [0,1) with 24-bit resolution (exact in fp32 and
+    fp64) for each env: value j comes from word j%4 of block j//4, counter =
+    (env_lo, env_hi, episode, stream*65536 + block), key = (seed_lo, seed_hi)."""
+    env_id = np.asarray(env_id, dtype=np.uint64)
+    episode = np.asarray(episode, dtype=np.uint64)
+    n = env_id.shape[0]
+    out = np.empty((n, n_values))
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    for blk in range((n_values + 3) // 4):
+        ctr = np.stack([env_id & _MASK32, env_id >> np.uint64(32), episode & _MASK32,
+                        np.full(n, stream * 65536 + blk, dtype=np.uint64)], axis=1).astype(np.uint32)
+        w = philox4x32(ctr, key)
+        for j in range(4):
+            if blk * 4 + j < n_values:
+                out[:, blk * 4 + j] = (w[:, j] >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+    return out
+
+
+# ==========================================================================
+# 6DoF env (vectorised; 6DoF.py:445-594)
+# ==========================================================================
+MODE_RPM, MODE_FORCE, MODE_PID = 0, 1, 2
+
+
+class Rov6EnvOracle:
+    """Vectorised restatement of BlueROV2Heavy6DoFEnv with the integrator fixed
+    to RK4 x n_sub.  ``mode``: 0 = action is 8 thruster rpm, 1 = action is a
+    6-vector of earth-frame generalised forces, 2 = the reference's Gym
+    semantics (action -> PID set-point, 6DoF.py:545-552).  Auto-reset (SB3
+    VecEnv convention) is a build addition; with ``auto_reset=False`` the env
+    behaves like the reference (state keeps integrating past ``done``)."""
+
+    def __init__(self, n, params=None, dt=0.2, max_steps=250, n_sub=8, mode=MODE_PID, seed=0,
+                 auto_reset=False, env_id0=0):
+        self.n, self.p = n, (params or Rov6Params())
+        self.dt, self.max_steps, self.n_sub, self.mode, self.seed = dt, max_steps, n_sub, mode, seed
+        self.auto_reset = auto_reset
+        self.env_ids = np.arange(env_id0, env_id0 + n, dtype=np.uint64)
+        self.episode = np.zeros(n, dtype=np.uint64)
+        self.fixed_sp = False
+        self.Minv = np.linalg.inv(self.p.mass_matrix())
+
+    # -- reset ------------------------------------------------------------
+    def _draw(self, idx):
+        """Random branch of reset (6DoF.py:493-501).  The reference's own line
+        raises (shape (2,3) minus (2,)); the build defines it as the 3-component
+        analogue of 3DoF.py:423: path = (U[0,1)^(2x3) - 0.5) * 10 and
+        targetOrientation = U[0,1)^3 * 2 pi, drawn from Philox."""
+        u = philox_uniform(self.seed, self.env_ids[idx], self.episode[idx], 9)
+        path = (u[:, :6] - 0.5) * 10.
+        orient = u[:, 6:9] * TWO_PI
+        return path, orient
+
+    def reset(self, initial_setpoint=None):
+        n = self.n
+        self.i_step = np.zeros(n, dtype=np.int64)
+        self.time = np.zeros(n)
+        self.state = np.zeros((n, 12))
+        self.path = np.zeros((n, 6))
+        if initial_setpoint is None:
+            path, orient = self._draw(np.arange(n))
+            self.path[:] = path
+            self.set_point = np.concatenate([path[:, :3], orient], axis=1)
+            self.fixed_sp = False
+        else:
+            sp = np.broadcast_to(np.asarray(initial_setpoint, dtype=float), (n, 6)).copy()
+            self.path[:, :3] = sp[:, :3]
+            self.path[:, 3:] = sp[:, :3]
+            self.set_point = sp
+            self.fixed_sp = True
+        self.ctrl = pid6_new_state(n)
+        self.gcf = np.zeros((n, 6))
+        self.cv = np.zeros((n, 8))
+        return self.observe()
+
+    def _reset_rows(self, idx):
+        self.episode[idx] += np.uint64(1)
+        self.i_step[idx] = 0
+        self.time[idx] = 0.
+        self.state[idx] = 0.
+        if not self.fixed_sp:
+            path, orient = self._draw(idx)
+            self.path[idx] = path
+            self.set_point[idx] = np.concatenate([path[:, :3], orient], axis=1)
+        for k in ("eOld", "eInt"):
+            self.ctrl[k][idx] = 0.
+        self.ctrl["has_old"][idx] = False
+        self.ctrl["tOld"][idx] = 0.
+        self.gcf[idx] = 0.
+        self.cv[idx] = 0.
+
+    # -- observation, 6DoF.py:467-483 (iWp is always 0) ------------------------
+    def observe(self):
+        s, L3 = self.state, self.p.Length * 3.
+        obs = np.concatenate([
+            (self.path[:, 0:3] - s[:, 0:3]) / L3,
+            (self.path[:, 3:6] - s[:, 0:3]) / L3,
+            angle_error(self.set_point[:, 3:6], s[:, 3:6]) / (45. / 180. * np.pi)], axis=1)
+        return np.clip(obs, -1., 1.)
+
+    # -- one derivative evaluation in the configured mode ------------------
+    def _f(self, action):
+        if self.mode == MODE_RPM:
+            def f(t, y):
+                self.cv = action
+                return derivs6_rpm(self.p, y, action)
+        elif self.mode == MODE_FORCE:
+            def f(t, y):
+                self.gcf = action
+                d, self.cv = derivs6_force(self.p, y, action, return_cv=True)
+                return d
+        else:
+            def f(t, y):
+                d, self.gcf, self.cv = derivs6_pid(self.p, t, y, self.ctrl, self.set_point, return_aux=True)
+                return d
+        return f
+
+    def step(self, action):
+        action = np.atleast_2d(np.asarray(action, dtype=float))
+        self.i_step += 1
+        self.time = self.time + self.dt
+        if self.mode == MODE_PID and not self.fixed_sp:  # 6DoF.py:545-552
+            L2 = 2. * self.p.Length
+            scale = np.array([L2, L2, L2, 45. / 180. * np.pi, 45. / 180. * np.pi, 45. / 180. * np.pi])
+            self.set_point = action * scale + self.state[:, :6]
+        y = rk4_advance(self._f(action), self.time - self.dt, self.state, self.dt, self.n_sub)
+        y[:, 3:6] = np.mod(y[:, 3:6], TWO_PI)  # 6DoF.py:560
+        self.state = y
+        obs = self.observe()
+        done = self.i_step >= self.max_steps
+        reward = np.zeros(self.n)
+        info = {}
+        if self.auto_reset and done.any():
+            idx = np.nonzero(done)[0]
+            info["terminal_observation"] = obs.copy()
+            self._reset_rows(idx)
+            obs = self.observe()
+        return obs, reward, done, info
+
+    def history_row(self):
+        """The 33 columns the reference appends per step, 6DoF.py:578-580."""
+        return np.concatenate([self.time[:, None], self.state, self.gcf, self.cv, self.set_point], axis=1)
