@@ -1,0 +1,181 @@
+/*
+ * mvrl.h - C ABI of libmvrl.so: B200-native batched BlueROV2 Heavy simulator.
+ *
+ * The reference (UnnamedMoose/MarineVehicleReinforcementLearning) is pure
+ * Python and has no FFI layer; its "operator interface" for this path is the
+ * Python class surface.  Each entry point below replaces the per-environment
+ * numpy code of one reference function, batched over N environments:
+ *
+ *   mvrl_rov6_derivs      BlueROV2Heavy6DoF.derivs / forceModel / allocateThrust
+ *                         dynamicsModel_BlueROV2_Heavy_6DoF.py:220-236, 253-442
+ *   mvrl_rov6_step        BlueROV2Heavy6DoFEnv.step + dataToState
+ *                         dynamicsModel_BlueROV2_Heavy_6DoF.py:467-483, 531-594
+ *   mvrl_rov6_reset       BlueROV2Heavy6DoFEnv.reset
+ *                         dynamicsModel_BlueROV2_Heavy_6DoF.py:485-529
+ *   mvrl_rov6_pid         BlueROV2Heavy6DoF_PID_controller.computeControlForces
+ *                         dynamicsModel_BlueROV2_Heavy_6DoF.py:43-73
+ *   mvrl_coordinate_transform / mvrl_angle_error / mvrl_body_axes
+ *                         resources.py:98-143 / resources.py:75-95 /
+ *                         dynamicsModel_BlueROV2_Heavy_6DoF.py:238-251
+ *   mvrl_rov3_*           dynamicsModel_BlueROV2_Heavy_3DoF.py:114-296, 397-514
+ *   mvrl_auv_*            tag_00_Dec2023_simpleControlTurbulence/verySimpleAuv.py:147-410
+ *                         and flowGenerator.py:53-136
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative MVRL_E* code on
+ *     failure; mvrl_last_error() returns a thread-local message.  No C++
+ *     exception crosses this boundary.
+ *   - all array pointers are DEVICE pointers on the handle's device unless the
+ *     name says "host".  Arrays are structure-of-arrays: field k of
+ *     environment i lives at base[k * ld + i] (ld >= n, the leading dimension).
+ *     Element type is float (dtype 0) or double (dtype 1) as fixed at create.
+ *   - the library allocates nothing per call, never synchronises, and launches
+ *     on the caller's stream (CUDA-graph capturable).
+ *   - a handle is not thread-safe; use one per GPU / process.
+ */
+#ifndef MVRL_H_
+#define MVRL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVRL_VERSION 100
+
+#define MVRL_OK 0
+#define MVRL_EINVAL (-1)   /* bad argument */
+#define MVRL_ECUDA (-2)    /* CUDA runtime error (message has the detail) */
+#define MVRL_ENODEV (-3)   /* no usable CUDA device */
+
+#define MVRL_F32 0
+#define MVRL_F64 1
+
+/* action semantics of the 6DoF step */
+#define MVRL_ACT_RPM 0       /* action = 8 thruster rpm (synthetic random-thruster workload) */
+#define MVRL_ACT_FORCE 1     /* action = 6 earth-frame generalised forces (stateless controller seam) */
+#define MVRL_ACT_SETPOINT 2  /* action in [-1,1]^6 -> PID set-point: the reference's Gym semantics */
+
+typedef void* mvrl_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define MVRL_API __attribute__((visibility("default")))
+#else
+#define MVRL_API
+#endif
+
+/* ---------------------------------------------------------------- 6DoF -- */
+
+/* Physical + derived constants of BlueROV2Heavy6DoF
+ * (dynamicsModel_BlueROV2_Heavy_6DoF.py:83-218).  Names follow the reference.
+ * Derived matrices are supplied by the host so that they are bit-identical to
+ * what numpy gives the reference (pinv / inv); mvrl_rov6_default_params fills
+ * everything natively for non-Python callers. */
+typedef struct MvrlRov6Params {
+    double rho_f, m, Length;
+    double CG[3], CB[3];
+    double I[9];                                  /* row-major 3x3 */
+    double Xudot, Yvdot, Zwdot, Kpdot, Mqdot, Nrdot; /* used by Ca (6DoF.py:334-341) */
+    /* linear damping, 6DoF.py:345-352 */
+    double Xu, Yv, Yp, Yr, Zw, Zq, Kv, Kp, Kr, Mw, Mq, Nv, Np, Nr;
+    /* quadratic damping, 6DoF.py:354-368 */
+    double Xuu, Yvv, Ypp, Yrr, Zww, Zqq, Kvv, Kpp, Krr, Mww, Mqq, Nvv, Npp, Nrr;
+    double W, B;                                  /* weight m*9.81 and buoyancy dispVol*rho_f*9.81 */
+    double thrust_coef;                           /* rho_f * D_thruster^4 * Kt_thruster */
+    double rpm_max, rpm_deadband;                 /* 3500, 300 (6DoF.py:271-275) */
+    double M[36];                                 /* Mrb + Ma, row-major (6DoF.py:286-299) */
+    double Minv[36];                              /* inverse of M */
+    double A[48];                                 /* 6x8 allocation matrix, row-major (resources.py:19-35) */
+    double Ainv[48];                              /* 8x6 pseudo-inverse, row-major */
+    /* PID controller, 6DoF.py:46-54 */
+    double pid_Kp[6], pid_Ki[6], pid_Kd[6], pid_windup[6], pid_max[6];
+    int disable_thrusters;                        /* BlueROV2Heavy6DoF(disableThrusters=...) */
+} MvrlRov6Params;
+
+typedef struct MvrlRov6Config {
+    int dtype;         /* MVRL_F32 / MVRL_F64 */
+    int action_mode;   /* MVRL_ACT_* */
+    int n_sub;         /* RK4 sub-steps per env step (>= 1) */
+    int max_steps;     /* done when iStep >= max_steps (6DoF.py:569-571) */
+    double dt;         /* env step, 0.2 in the reference */
+    uint64_t seed;     /* Philox key for the random reset branch */
+    uint64_t env_id0;  /* global id of environment 0 of this shard (results independent of sharding) */
+    int auto_reset;    /* 1: SB3-VecEnv style reset inside the step kernel; 0: reference behaviour */
+    int fixed_sp;      /* 1: reset(initialSetpoint=...) mode, actions ignored (6DoF.py:536-541) */
+    int device;        /* CUDA device ordinal */
+    int fast_math;     /* fp32 only: 1 = MUFU sin/cos + approximate reciprocal */
+} MvrlRov6Config;
+
+/* Device buffers of one batch of 6DoF environments.  T = element type.
+ * Nullable members may be NULL. */
+typedef struct MvrlRov6Buffers {
+    void* state;        /* T [12][ld] x y z phi theta psi u v w p q r       in/out */
+    void* action;       /* T [8|6][ld] per action_mode                       in     */
+    void* obs;          /* T [9][ld]  6DoF.py:467-483                        out    */
+    void* reward;       /* T [ld]     (identically 0, 6DoF.py:575)           out    */
+    uint8_t* done;      /* [ld]                                              out    */
+    int32_t* istep;     /* [ld]       iStep                                  in/out */
+    void* setpoint;     /* T [6][ld]  controller.setPoint                    in/out */
+    void* path;         /* T [6][ld]  path[0,:], path[1,:]                   in (out on reset) */
+    void* ctrl;         /* T [13][ld] eOld(6) eInt(6) tOld; eOld[0]=NaN <=> eOld is None;
+                           required for MVRL_ACT_SETPOINT, else nullable     in/out */
+    uint32_t* episode;  /* [ld] episode counter (Philox stream); nullable iff !auto_reset */
+    void* terminal_obs; /* T [9][ld] obs before auto-reset, written where done; nullable */
+    void* aux;          /* T [14][ld] generalisedControlForces(6), controlVector(8) of the
+                           last derivative evaluation (6DoF.py:578-580); nullable */
+    double* ep_stats;   /* [8]: episodes, sum length, sum return, min return, max return,
+                           non-finite states, 0, 0 - accumulated atomically; nullable */
+} MvrlRov6Buffers;
+
+typedef struct MvrlRov6 MvrlRov6;
+
+MVRL_API int mvrl_version(void);
+MVRL_API const char* mvrl_last_error(void);
+MVRL_API int mvrl_device_count(void);
+
+MVRL_API int mvrl_rov6_default_params(MvrlRov6Params* out);
+MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, const MvrlRov6Config* cfg);
+MVRL_API int mvrl_rov6_destroy(MvrlRov6* h);
+/* 1 if the handle runs the kernels specialised for the reference's default
+ * sparsity pattern (CG on the z axis, diagonal inertia, no cross damping but
+ * Mww, neutral buoyancy, default allocation pattern), 0 for the generic ones */
+MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h);
+
+/* One derivative evaluation per environment (debug / parity entry, K2).
+ *   state  T [12][ld]; dstate T [12][ld]
+ *   act    per action_mode: rpm T [8][ld] | force T [6][ld] | (SETPOINT) unused
+ *   t      T [ld], setpoint T [6][ld], ctrl T [13][ld]: SETPOINT mode only (ctrl is
+ *          updated exactly like the reference mutates its controller, 6DoF.py:62-71)
+ *   aux    nullable T [50][ld]: RHS(6) gcf(6) rpm(8) then the five retComp columns
+ *          -Crb v, -Ca v, -D v, G, H (6 each), 6DoF.py:401-402 */
+MVRL_API int mvrl_rov6_derivs(MvrlRov6* h, int64_t n, int64_t ld, const void* state, const void* act,
+                     const void* t, const void* setpoint, void* ctrl, void* dstate, void* aux,
+                     mvrl_stream_t stream);
+
+/* One env step for n environments (K1). */
+MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream);
+
+/* reset(): mask nullable (= all).  initial_setpoint: 6 host doubles or NULL for
+ * the random branch (path and target orientation drawn from Philox). */
+MVRL_API int mvrl_rov6_reset(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const uint8_t* mask,
+                    const double* initial_setpoint_host, mvrl_stream_t stream);
+
+/* Stand-alone PID evaluation: pose T [6][ld], t T [ld], setpoint T [6][ld],
+ * ctrl T [13][ld] in/out, forces T [6][ld] out. */
+MVRL_API int mvrl_rov6_pid(MvrlRov6* h, int64_t n, int64_t ld, const void* pose, const void* t, const void* setpoint,
+                  void* ctrl, void* forces, mvrl_stream_t stream);
+
+/* ------------------------------------------------------- resources.py -- */
+/* J(phi,theta,psi): out T [dof*dof][ld] row-major entries, dof = 3 or 6 */
+MVRL_API int mvrl_coordinate_transform(int dtype, int dof, int64_t n, int64_t ld, const void* phi, const void* theta,
+                              const void* psi, void* out, mvrl_stream_t stream);
+MVRL_API int mvrl_angle_error(int dtype, int64_t n, const void* psi_d, const void* psi, void* out, mvrl_stream_t stream);
+/* iHat jHat kHat: out T [9][ld] */
+MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const void* angles /* T [3][ld] */, void* out,
+                   mvrl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVRL_H_ */

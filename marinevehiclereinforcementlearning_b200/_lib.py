@@ -1,0 +1,138 @@
+"""ctypes binding of libmvrl.so (C ABI declared in include/mvrl.h).
+
+There is deliberately no CPU implementation behind this module: if the shared
+library is missing, or no CUDA device is present, every compute entry point
+raises ``RuntimeError``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libmvrl.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+F32, F64 = 0, 1
+ACT_RPM, ACT_FORCE, ACT_SETPOINT = 0, 1, 2
+
+_d = C.c_double
+
+
+class MvrlRov6Params(C.Structure):
+    _fields_ = [
+        ("rho_f", _d), ("m", _d), ("Length", _d),
+        ("CG", _d * 3), ("CB", _d * 3), ("I", _d * 9),
+        ("Xudot", _d), ("Yvdot", _d), ("Zwdot", _d), ("Kpdot", _d), ("Mqdot", _d), ("Nrdot", _d),
+        ("Xu", _d), ("Yv", _d), ("Yp", _d), ("Yr", _d), ("Zw", _d), ("Zq", _d), ("Kv", _d),
+        ("Kp", _d), ("Kr", _d), ("Mw", _d), ("Mq", _d), ("Nv", _d), ("Np", _d), ("Nr", _d),
+        ("Xuu", _d), ("Yvv", _d), ("Ypp", _d), ("Yrr", _d), ("Zww", _d), ("Zqq", _d), ("Kvv", _d),
+        ("Kpp", _d), ("Krr", _d), ("Mww", _d), ("Mqq", _d), ("Nvv", _d), ("Npp", _d), ("Nrr", _d),
+        ("W", _d), ("B", _d), ("thrust_coef", _d), ("rpm_max", _d), ("rpm_deadband", _d),
+        ("M", _d * 36), ("Minv", _d * 36), ("A", _d * 48), ("Ainv", _d * 48),
+        ("pid_Kp", _d * 6), ("pid_Ki", _d * 6), ("pid_Kd", _d * 6), ("pid_windup", _d * 6), ("pid_max", _d * 6),
+        ("disable_thrusters", C.c_int),
+    ]
+
+
+class MvrlRov6Config(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("action_mode", C.c_int), ("n_sub", C.c_int), ("max_steps", C.c_int),
+        ("dt", _d), ("seed", C.c_uint64), ("env_id0", C.c_uint64),
+        ("auto_reset", C.c_int), ("fixed_sp", C.c_int), ("device", C.c_int), ("fast_math", C.c_int),
+    ]
+
+
+class MvrlRov6Buffers(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p), ("action", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("istep", C.c_void_p), ("setpoint", C.c_void_p), ("path", C.c_void_p),
+        ("ctrl", C.c_void_p), ("episode", C.c_void_p), ("terminal_obs", C.c_void_p), ("aux", C.c_void_p),
+        ("ep_stats", C.c_void_p),
+    ]
+
+
+_vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
+
+# name -> (restype, argtypes); every symbol include/mvrl.h declares
+PROTOTYPES = {
+    "mvrl_version": (_int, []),
+    "mvrl_last_error": (C.c_char_p, []),
+    "mvrl_device_count": (_int, []),
+    "mvrl_rov6_default_params": (_int, [C.POINTER(MvrlRov6Params)]),
+    "mvrl_rov6_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlRov6Params), C.POINTER(MvrlRov6Config)]),
+    "mvrl_rov6_destroy": (_int, [_vp]),
+    "mvrl_rov6_is_specialised": (_int, [_vp]),
+    "mvrl_rov6_derivs": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_rov6_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp]),
+    "mvrl_rov6_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp, C.POINTER(_d), _vp]),
+    "mvrl_rov6_pid": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_coordinate_transform": (_int, [_int, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_angle_error": (_int, [_int, _i64, _vp, _vp, _vp, _vp]),
+    "mvrl_body_axes": (_int, [_int, _i64, _i64, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libmvrl.so in-tree with nvcc for sm_100a (csrc/Makefile)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libmvrl.so failed (see output above)")
+    return LIB_PATH
+
+
+def load():
+    """Load libmvrl.so and bind every prototype.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libmvrl.so is not built (%s). Build it with `make -C %s` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % (LIB_PATH, CSRC_DIR))
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mvrl_version() != 100:
+        raise RuntimeError("libmvrl.so version %d does not match the Python binding (100)" % lib.mvrl_version())
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().mvrl_last_error().decode("utf-8", "replace")
+        raise RuntimeError("libmvrl error %d: %s" % (rc, msg))
+
+
+def require_cuda():
+    """The product path needs a GPU; fail loudly otherwise."""
+    import torch
+    if not torch.cuda.is_available() or load().mvrl_device_count() == 0:
+        raise RuntimeError("marinevehiclereinforcementlearning_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def torch_dtype_code(dtype):
+    import torch
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.float64:
+        return F64
+    raise ValueError("dtype must be torch.float32 or torch.float64, got %r" % (dtype,))

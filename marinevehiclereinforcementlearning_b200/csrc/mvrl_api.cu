@@ -1,0 +1,442 @@
+// C ABI of libmvrl.so (see include/mvrl.h).  Host side: argument checking,
+// conversion of the vehicle constants to the compute type, kernel selection
+// (dtype x action mode x default-sparsity x fast-math) and launches on the
+// caller's stream.  No allocation, no synchronisation per call.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/mvrl.h"
+#include "rov6_kernels.cuh"
+
+using namespace mvrl;
+
+// ---------------------------------------------------------------------------
+// error reporting
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int mvrl_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MVRL_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return mvrl_fail(MVRL_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" MVRL_API int mvrl_version(void) { return MVRL_VERSION; }
+extern "C" MVRL_API const char* mvrl_last_error(void) { return g_err; }
+extern "C" MVRL_API int mvrl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// small dense linear algebra for mvrl_rov6_default_params (host, long double)
+// ---------------------------------------------------------------------------
+static bool invert_n(const double* a, double* out, int n) {
+    long double w[6][12];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) { w[i][j] = a[i * n + j]; w[i][n + j] = (i == j) ? 1.0L : 0.0L; }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabsl(w[r][c]) > fabsl(w[piv][c])) piv = r;
+        if (fabsl(w[piv][c]) < 1e-300L) return false;
+        if (piv != c) for (int j = 0; j < 2 * n; ++j) { long double t = w[c][j]; w[c][j] = w[piv][j]; w[piv][j] = t; }
+        const long double d = w[c][c];
+        for (int j = 0; j < 2 * n; ++j) w[c][j] /= d;
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const long double f = w[r][c];
+            if (f != 0.0L) for (int j = 0; j < 2 * n; ++j) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) out[i * n + j] = (double)w[i][n + j];
+    return true;
+}
+
+extern "C" MVRL_API int mvrl_rov6_default_params(MvrlRov6Params* p) {
+    if (!p) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_default_params: null output");
+    memset(p, 0, sizeof(*p));
+    const double pi = 3.14159265358979323846;
+    // dynamicsModel_BlueROV2_Heavy_6DoF.py:83-184
+    p->rho_f = 1000.; p->m = 11.4; p->Length = 0.457;
+    p->CG[2] = 0.05;
+    p->I[0] = p->I[4] = p->I[8] = 0.16;
+    p->Xudot = -5.5; p->Yvdot = -12.7; p->Zwdot = -14.57; p->Kpdot = p->Mqdot = p->Nrdot = -0.12;
+    p->Xuu = -18.18; p->Yvv = -21.66; p->Zww = -36.99; p->Kpp = p->Mqq = p->Nrr = -1.55; p->Mww = -1.55;
+    p->Xu = -4.03; p->Yv = -6.22; p->Zw = -5.18; p->Kp = p->Mq = p->Nr = -0.07;
+    const double dispVol = p->m / p->rho_f;
+    p->W = p->m * 9.81;
+    p->B = dispVol * p->rho_f * 9.81;
+    const double D = 0.1;
+    const double Kt = 40. / (1000. * pow(3500. / 60., 2.) * pow(D, 4.));
+    p->thrust_coef = p->rho_f * pow(D, 4.) * Kt;
+    p->rpm_max = 3500.; p->rpm_deadband = 300.;
+    // M = Mrb + Ma with Ma[2][2] = -Zvdot = 0 (6DoF.py:286-299)
+    const double m = p->m, xg = p->CG[0], yg = p->CG[1], zg = p->CG[2];
+    const double Mrb[36] = {m, 0, 0, 0, m * zg, -m * yg,  0, m, 0, -m * zg, 0, m * xg,  0, 0, m, m * yg, -m * xg, 0,
+                            0, -m * zg, m * yg, p->I[0], p->I[1], p->I[2],  m * zg, 0, -m * xg, p->I[3], p->I[4], p->I[5],
+                            -m * yg, m * xg, 0, p->I[6], p->I[7], p->I[8]};
+    const double Zvdot = 0.;
+    const double Ma[6] = {-p->Xudot, -p->Yvdot, -Zvdot, -p->Kpdot, -p->Mqdot, -p->Nrdot};
+    for (int i = 0; i < 36; ++i) p->M[i] = Mrb[i];
+    for (int i = 0; i < 6; ++i) p->M[i * 6 + i] += Ma[i];
+    if (!invert_n(p->M, p->Minv, 6)) return mvrl_fail(MVRL_EINVAL, "singular mass matrix");
+    // thruster geometry, 6DoF.py:164-212, and allocation, resources.py:19-35
+    const double al = 33. / 180. * pi, lx = 0.1475, ly = 0.101, lz = 0.068, lxv = 0.120, lyv = 0.22, lzv = 0.0;
+    const double pos[8][3] = {{lx, ly, lz}, {lx, -ly, lz}, {-lx, ly, lz}, {-lx, -ly, lz},
+                              {lxv, lyv, lzv}, {lxv, -lyv, lzv}, {-lxv, lyv, lzv}, {-lxv, -lyv, lzv}};
+    const double nrm[8][3] = {{cos(al), -sin(al), 0}, {cos(al), sin(al), 0}, {-cos(al), -sin(al), 0}, {-cos(al), sin(al), 0},
+                              {0, 0, -1}, {0, 0, 1}, {0, 0, 1}, {0, 0, -1}};
+    for (int i = 0; i < 8; ++i) {
+        const double* r = pos[i]; const double* n = nrm[i];
+        p->A[0 * 8 + i] = n[0]; p->A[1 * 8 + i] = n[1]; p->A[2 * 8 + i] = n[2];
+        p->A[3 * 8 + i] = r[1] * n[2] - r[2] * n[1];
+        p->A[4 * 8 + i] = r[2] * n[0] - r[0] * n[2];
+        p->A[5 * 8 + i] = r[0] * n[1] - r[1] * n[0];
+    }
+    // A has full row rank: pinv(A) = A^T (A A^T)^-1
+    double AAt[36], AAtInv[36];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+        long double s = 0; for (int k = 0; k < 8; ++k) s += (long double)p->A[i * 8 + k] * p->A[j * 8 + k];
+        AAt[i * 6 + j] = (double)s;
+    }
+    if (!invert_n(AAt, AAtInv, 6)) return mvrl_fail(MVRL_EINVAL, "rank-deficient allocation matrix");
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 6; ++j) {
+        long double s = 0; for (int k = 0; k < 6; ++k) s += (long double)p->A[k * 8 + i] * AAtInv[k * 6 + j];
+        p->Ainv[i * 6 + j] = (double)s;
+    }
+    // PID, 6DoF.py:46-54
+    const double wind[6] = {2., 2., 2., 90. / 180. * pi, 90. / 180. * pi, 90. / 180. * pi};
+    const double fmx[6] = {50., 50., 50., 1., 1., 2.};
+    const double kp[6] = {25., 25., 25., 10., 10., 1.}, ki[6] = {2., 2., 2., 0.1, 0.1, 0.2}, kd[6] = {20., 20., 20., 5., 5., 0.65};
+    for (int i = 0; i < 6; ++i) { p->pid_windup[i] = wind[i]; p->pid_max[i] = fmx[i]; p->pid_Kp[i] = kp[i]; p->pid_Ki[i] = ki[i]; p->pid_Kd[i] = kd[i]; }
+    p->disable_thrusters = 0;
+    return MVRL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct MvrlRov6 {
+    MvrlRov6Params p;
+    MvrlRov6Config c;
+    bool sp;  // default sparsity pattern holds -> specialised kernels
+    Rov6Dev<float> pf;
+    Rov6Dev<double> pd;
+};
+
+template <typename T> static void to_dev(const MvrlRov6Params& p, Rov6Dev<T>& d) {
+    const double pi = 3.14159265358979323846;
+    d.m = T(p.m); d.xg = T(p.CG[0]); d.yg = T(p.CG[1]); d.zg = T(p.CG[2]);
+    d.Ixx = T(p.I[0]); d.Iyy = T(p.I[4]); d.Izz = T(p.I[8]); d.Ixy = T(p.I[1]); d.Ixz = T(p.I[2]); d.Iyz = T(p.I[5]);
+    d.Xud = T(p.Xudot); d.Yvd = T(p.Yvdot); d.Zwd = T(p.Zwdot); d.Kpd = T(p.Kpdot); d.Mqd = T(p.Mqdot); d.Nrd = T(p.Nrdot);
+    d.Xu = T(p.Xu); d.Yv = T(p.Yv); d.Yp = T(p.Yp); d.Yr = T(p.Yr); d.Zw = T(p.Zw); d.Zq = T(p.Zq); d.Kv = T(p.Kv);
+    d.Kp = T(p.Kp); d.Kr = T(p.Kr); d.Mw = T(p.Mw); d.Mq = T(p.Mq); d.Nv = T(p.Nv); d.Np = T(p.Np); d.Nr = T(p.Nr);
+    d.Xuu = T(p.Xuu); d.Yvv = T(p.Yvv); d.Ypp = T(p.Ypp); d.Yrr = T(p.Yrr); d.Zww = T(p.Zww); d.Zqq = T(p.Zqq); d.Kvv = T(p.Kvv);
+    d.Kpp = T(p.Kpp); d.Krr = T(p.Krr); d.Mww = T(p.Mww); d.Mqq = T(p.Mqq); d.Nvv = T(p.Nvv); d.Npp = T(p.Npp); d.Nrr = T(p.Nrr);
+    d.WmB = T(p.W - p.B);
+    d.gx = T(p.CG[0] * p.W - p.CB[0] * p.B); d.gy = T(p.CG[1] * p.W - p.CB[1] * p.B); d.gz = T(p.CG[2] * p.W - p.CB[2] * p.B);
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 8; ++j) d.A[i][j] = T(p.A[i * 8 + j]);
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 6; ++j) d.Ainv[i][j] = T(p.Ainv[i * 6 + j]);
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) d.Minv[i][j] = T(p.Minv[i * 6 + j]);
+    d.thrust_k = T(p.thrust_coef / 3600.);
+    d.inv_thrust_coef = T(1. / p.thrust_coef);
+    d.rpm_max = T(p.rpm_max); d.rpm_db = T(p.rpm_deadband);
+    d.f_max = T(p.thrust_coef * (p.rpm_max / 60.) * (p.rpm_max / 60.));
+    d.f_db = T(p.thrust_coef * (p.rpm_deadband / 60.) * (p.rpm_deadband / 60.));
+    for (int i = 0; i < 6; ++i) {
+        d.pKp[i] = T(p.pid_Kp[i]); d.pKi[i] = T(p.pid_Ki[i]); d.pKd[i] = T(p.pid_Kd[i]);
+        d.pWind[i] = T(p.pid_windup[i]); d.pMax[i] = T(p.pid_max[i]);
+    }
+    d.inv_3L = T(1. / (p.Length * 3.)); d.act_pos = T(2. * p.Length);
+    d.act_ang = T(45. / 180. * pi); d.inv_ang = T(1. / (45. / 180. * pi));
+    d.thrusters_on = p.disable_thrusters ? 0 : 1;
+}
+
+// Does the parameter set have the reference's default sparsity?  (Tiny pinv /
+// inverse round-off entries count as zero; they are < 1e-13 of the scale.)
+static bool default_sparsity(const MvrlRov6Params& p) {
+    auto z = [](double v, double scale) { return fabs(v) <= 1e-13 * scale; };
+    if (p.CG[0] != 0 || p.CG[1] != 0 || p.CB[0] != 0 || p.CB[1] != 0) return false;
+    if (p.I[1] != 0 || p.I[2] != 0 || p.I[5] != 0 || p.I[3] != 0 || p.I[6] != 0 || p.I[7] != 0) return false;
+    if (p.W - p.B != 0) return false;
+    if (p.Yp != 0 || p.Yr != 0 || p.Zq != 0 || p.Kv != 0 || p.Kr != 0 || p.Mw != 0 || p.Nv != 0 || p.Np != 0) return false;
+    if (p.Ypp != 0 || p.Yrr != 0 || p.Zqq != 0 || p.Kvv != 0 || p.Krr != 0 || p.Nvv != 0 || p.Npp != 0) return false;
+    double amax = 0, imax = 0, mmax = 0;
+    for (int i = 0; i < 48; ++i) { amax = fmax(amax, fabs(p.A[i])); imax = fmax(imax, fabs(p.Ainv[i])); }
+    for (int i = 0; i < 36; ++i) mmax = fmax(mmax, fabs(p.Minv[i]));
+    for (int j = 0; j < 8; ++j) {
+        const bool horiz = j < 4;
+        if (horiz ? !z(p.A[2 * 8 + j], amax) : !(z(p.A[0 * 8 + j], amax) && z(p.A[1 * 8 + j], amax) && z(p.A[5 * 8 + j], amax))) return false;
+        if (horiz ? !(z(p.Ainv[j * 6 + 2], imax) && z(p.Ainv[j * 6 + 3], imax) && z(p.Ainv[j * 6 + 4], imax)) : !z(p.Ainv[j * 6 + 5], imax)) return false;
+    }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+        const bool keep = (i == j) || (i == 0 && j == 4) || (i == 4 && j == 0) || (i == 1 && j == 3) || (i == 3 && j == 1);
+        if (!keep && !z(p.Minv[i * 6 + j], mmax)) return false;
+    }
+    return true;
+}
+
+extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, const MvrlRov6Config* cfg) {
+    if (!out || !params || !cfg) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_create: null argument");
+    if (cfg->dtype != MVRL_F32 && cfg->dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "dtype must be MVRL_F32 or MVRL_F64");
+    if (cfg->action_mode < 0 || cfg->action_mode > 2) return mvrl_fail(MVRL_EINVAL, "bad action_mode %d", cfg->action_mode);
+    if (cfg->n_sub < 1) return mvrl_fail(MVRL_EINVAL, "n_sub must be >= 1");
+    if (!(cfg->dt > 0)) return mvrl_fail(MVRL_EINVAL, "dt must be > 0");
+    if (!(params->thrust_coef > 0)) return mvrl_fail(MVRL_EINVAL, "thrust_coef must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return mvrl_fail(MVRL_ENODEV, "no CUDA device: libmvrl has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return mvrl_fail(MVRL_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    MvrlRov6* h = new (std::nothrow) MvrlRov6();
+    if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
+    h->p = *params;
+    h->c = *cfg;
+    h->sp = default_sparsity(*params);
+    to_dev(*params, h->pf);
+    to_dev(*params, h->pd);
+    *out = h;
+    return MVRL_OK;
+}
+
+extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) { delete h; return MVRL_OK; }
+extern "C" MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h) { return (h && h->sp) ? 1 : 0; }
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { cudaGetLastError(); return mvrl_fail(MVRL_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e)); }
+    return MVRL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// step
+// ---------------------------------------------------------------------------
+template <typename T, int MODE, bool SP, bool FAST>
+static void launch_step(const Rov6StepArgs<T>& a, cudaStream_t s) {
+    rov6_step_kernel<T, MODE, SP, FAST><<<grid_for(a.n, 128), 128, 0, s>>>(a);
+}
+template <typename T, bool FAST>
+static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, cudaStream_t s) {
+    switch (mode * 2 + (sp ? 1 : 0)) {
+        case 0: launch_step<T, ACT_RPM, false, FAST>(a, s); break;
+        case 1: launch_step<T, ACT_RPM, true, FAST>(a, s); break;
+        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, s); break;
+        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, s); break;
+        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, s); break;
+        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, s); break;
+    }
+}
+
+template <typename T>
+static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t n, int64_t ld, const MvrlRov6Buffers* b, Rov6StepArgs<T>& a) {
+    a.P = P; a.n = n; a.ld = ld;
+    a.state = (T*)b->state; a.action = (const T*)b->action; a.obs = (T*)b->obs; a.reward = (T*)b->reward;
+    a.done = b->done; a.istep = b->istep; a.setpoint = (T*)b->setpoint; a.path = (T*)b->path; a.ctrl = (T*)b->ctrl;
+    a.episode = b->episode; a.term_obs = (T*)b->terminal_obs; a.aux = (T*)b->aux; a.stats = b->ep_stats;
+    a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub);
+    a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
+    a.seed = h->c.seed; a.env_id0 = h->c.env_id0;
+    a.auto_reset = h->c.auto_reset; a.fixed_sp = h->c.fixed_sp;
+}
+
+extern "C" MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
+    if (!h || !b) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: null argument");
+    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: need 0 <= n <= ld (n=%lld ld=%lld)", (long long)n, (long long)ld);
+    if (!b->state || !b->action || !b->obs || !b->reward || !b->done || !b->istep || !b->setpoint || !b->path)
+        return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: state/action/obs/reward/done/istep/setpoint/path are required");
+    if (h->c.action_mode == MVRL_ACT_SETPOINT && !b->ctrl) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: ctrl is required in set-point mode");
+    if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: episode is required with auto_reset");
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->c.dtype == MVRL_F64) {
+        Rov6StepArgs<double> a; fill_step_args(h, h->pd, n, ld, b, a);
+        dispatch_step<double, false>(a, h->c.action_mode, h->sp, s);
+    } else {
+        Rov6StepArgs<float> a; fill_step_args(h, h->pf, n, ld, b, a);
+        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, s);
+        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, s);
+    }
+    return check_launch("rov6_step");
+}
+
+// ---------------------------------------------------------------------------
+// derivs
+// ---------------------------------------------------------------------------
+template <typename T>
+static int derivs_impl(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t n, int64_t ld, const void* state, const void* act, const void* t,
+                       const void* setpoint, void* ctrl, void* dstate, void* aux, cudaStream_t s) {
+    Rov6DerivArgs<T> a;
+    a.P = P; a.n = n; a.ld = ld; a.state = (const T*)state; a.act = (const T*)act; a.t = (const T*)t;
+    a.setpoint = (const T*)setpoint; a.ctrl = (T*)ctrl; a.dstate = (T*)dstate; a.aux = (T*)aux;
+    const unsigned g = grid_for(n, 128);
+    switch (h->c.action_mode * 2 + (h->sp ? 1 : 0)) {
+        case 0: rov6_derivs_kernel<T, ACT_RPM, false><<<g, 128, 0, s>>>(a); break;
+        case 1: rov6_derivs_kernel<T, ACT_RPM, true><<<g, 128, 0, s>>>(a); break;
+        case 2: rov6_derivs_kernel<T, ACT_FORCE, false><<<g, 128, 0, s>>>(a); break;
+        case 3: rov6_derivs_kernel<T, ACT_FORCE, true><<<g, 128, 0, s>>>(a); break;
+        case 4: rov6_derivs_kernel<T, ACT_SETPOINT, false><<<g, 128, 0, s>>>(a); break;
+        default: rov6_derivs_kernel<T, ACT_SETPOINT, true><<<g, 128, 0, s>>>(a); break;
+    }
+    return check_launch("rov6_derivs");
+}
+
+extern "C" MVRL_API int mvrl_rov6_derivs(MvrlRov6* h, int64_t n, int64_t ld, const void* state, const void* act, const void* t,
+                                const void* setpoint, void* ctrl, void* dstate, void* aux, mvrl_stream_t stream) {
+    if (!h || !state || !dstate) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_derivs: null argument");
+    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_derivs: need 0 <= n <= ld");
+    if (h->c.action_mode == MVRL_ACT_SETPOINT) {
+        if (!t || !setpoint || !ctrl) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_derivs: t, setpoint and ctrl are required in set-point mode");
+    } else if (!act) {
+        return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_derivs: act is required");
+    }
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->c.dtype == MVRL_F64) return derivs_impl<double>(h, h->pd, n, ld, state, act, t, setpoint, ctrl, dstate, aux, s);
+    return derivs_impl<float>(h, h->pf, n, ld, state, act, t, setpoint, ctrl, dstate, aux, s);
+}
+
+// ---------------------------------------------------------------------------
+// reset / pid
+// ---------------------------------------------------------------------------
+template <typename T>
+static int reset_impl(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const uint8_t* mask,
+                      const double* init_sp, cudaStream_t s) {
+    Rov6ResetArgs<T> a;
+    a.P = P; a.n = n; a.ld = ld;
+    a.state = (T*)b->state; a.obs = (T*)b->obs; a.istep = b->istep; a.setpoint = (T*)b->setpoint; a.path = (T*)b->path;
+    a.ctrl = (T*)b->ctrl; a.episode = b->episode; a.aux = (T*)b->aux; a.mask = mask;
+    a.has_init_sp = init_sp ? 1 : 0;
+    for (int k = 0; k < 6; ++k) a.init_sp[k] = init_sp ? T(init_sp[k]) : T(0);
+    a.seed = h->c.seed; a.env_id0 = h->c.env_id0;
+    rov6_reset_kernel<T><<<grid_for(n, 128), 128, 0, s>>>(a);
+    return check_launch("rov6_reset");
+}
+
+extern "C" MVRL_API int mvrl_rov6_reset(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const uint8_t* mask,
+                               const double* initial_setpoint_host, mvrl_stream_t stream) {
+    if (!h || !b) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_reset: null argument");
+    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_reset: need 0 <= n <= ld");
+    if (!b->state || !b->obs || !b->istep || !b->setpoint || !b->path)
+        return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_reset: state/obs/istep/setpoint/path are required");
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->c.dtype == MVRL_F64) return reset_impl<double>(h, h->pd, n, ld, b, mask, initial_setpoint_host, s);
+    return reset_impl<float>(h, h->pf, n, ld, b, mask, initial_setpoint_host, s);
+}
+
+template <typename T>
+static int pid_impl(const Rov6Dev<T>& P, int64_t n, int64_t ld, const void* pose, const void* t, const void* sp, void* ctrl, void* forces, cudaStream_t s) {
+    Rov6PidArgs<T> a;
+    a.P = P; a.n = n; a.ld = ld; a.pose = (const T*)pose; a.t = (const T*)t; a.setpoint = (const T*)sp; a.ctrl = (T*)ctrl; a.forces = (T*)forces;
+    rov6_pid_kernel<T><<<grid_for(n, 128), 128, 0, s>>>(a);
+    return check_launch("rov6_pid");
+}
+
+extern "C" MVRL_API int mvrl_rov6_pid(MvrlRov6* h, int64_t n, int64_t ld, const void* pose, const void* t, const void* setpoint,
+                             void* ctrl, void* forces, mvrl_stream_t stream) {
+    if (!h || !pose || !t || !setpoint || !ctrl || !forces) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_pid: null argument");
+    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_pid: need 0 <= n <= ld");
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    if (h->c.dtype == MVRL_F64) return pid_impl<double>(h->pd, n, ld, pose, t, setpoint, ctrl, forces, (cudaStream_t)stream);
+    return pid_impl<float>(h->pf, n, ld, pose, t, setpoint, ctrl, forces, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// resources.py helpers
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void coordinate_transform_kernel(int dof, long n, long ld, const T* phi, const T* theta, const T* psi, T* out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (dof == 3) {  // resources.py:108-113
+        T s, c;
+        Real<T>::sincos(psi[i], &s, &c);
+        const T J[9] = {c, -s, T(0), s, c, T(0), T(0), T(0), T(1)};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[k * ld + i] = J[k];
+        return;
+    }
+    // resources.py:115-141: J = blkdiag(J1, J2), obtained column by column from kinematics6
+    const Trig6<T> g = trig6<T, false>(phi[i], theta[i], psi[i]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        T nu[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        nu[c] = T(1);
+        T ed[6];
+        kinematics6<T, false>(g, nu, ed);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) out[(r * 6 + c) * ld + i] = ed[r];
+    }
+}
+
+extern "C" MVRL_API int mvrl_coordinate_transform(int dtype, int dof, int64_t n, int64_t ld, const void* phi, const void* theta,
+                                         const void* psi, void* out, mvrl_stream_t stream) {
+    if ((dof != 3 && dof != 6) || !psi || !out || (dof == 6 && (!phi || !theta))) return mvrl_fail(MVRL_EINVAL, "mvrl_coordinate_transform: bad argument");
+    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_coordinate_transform: need 0 <= n <= ld");
+    if (n == 0) return MVRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) coordinate_transform_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(dof, n, ld, (const double*)phi, (const double*)theta, (const double*)psi, (double*)out);
+    else if (dtype == MVRL_F32) coordinate_transform_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(dof, n, ld, (const float*)phi, (const float*)theta, (const float*)psi, (float*)out);
+    else return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    return check_launch("coordinate_transform");
+}
+
+template <typename T>
+__global__ void angle_error_kernel(long n, const T* a, const T* b, T* out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = angle_error(a[i], b[i]);
+}
+
+extern "C" MVRL_API int mvrl_angle_error(int dtype, int64_t n, const void* psi_d, const void* psi, void* out, mvrl_stream_t stream) {
+    if (!psi_d || !psi || !out || n < 0) return mvrl_fail(MVRL_EINVAL, "mvrl_angle_error: bad argument");
+    if (n == 0) return MVRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) angle_error_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, (const double*)psi_d, (const double*)psi, (double*)out);
+    else if (dtype == MVRL_F32) angle_error_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, (const float*)psi_d, (const float*)psi, (float*)out);
+    else return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    return check_launch("angle_error");
+}
+
+template <typename T>
+__global__ void body_axes_kernel(long n, long ld, const T* ang, T* out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Trig6<T> g = trig6<T, false>(ang[i], ang[ld + i], ang[2 * ld + i]);
+    // rows of R^T for R = Rx(phi) Ry(theta) Rz(psi), 6DoF.py:242
+    const T ax[9] = {g.cth * g.cps, g.cph * g.sps + g.sph * g.sth * g.cps, g.sph * g.sps - g.cph * g.sth * g.cps,
+                     -g.cth * g.sps, g.cph * g.cps - g.sph * g.sth * g.sps, g.sph * g.cps + g.cph * g.sth * g.sps,
+                     g.sth, -g.sph * g.cth, g.cph * g.cth};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k * ld + i] = ax[k];
+}
+
+extern "C" MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const void* angles, void* out, mvrl_stream_t stream) {
+    if (!angles || !out || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_body_axes: bad argument");
+    if (n == 0) return MVRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) body_axes_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)angles, (double*)out);
+    else if (dtype == MVRL_F32) body_axes_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)angles, (float*)out);
+    else return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    return check_launch("body_axes");
+}

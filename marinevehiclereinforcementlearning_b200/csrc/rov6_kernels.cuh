@@ -1,0 +1,395 @@
+// Kernels of the 6DoF path: K1 rov6_step (fused env step), K2 rov6_derivs
+// (parity/debug entry), reset and stand-alone PID.  One environment per
+// thread; SoA global layout [field][ld] so that every warp-level load/store is
+// one fully coalesced 128 B (fp32) / 256 B (fp64) transaction.
+#pragma once
+#include "rov6_model.cuh"
+
+namespace mvrl {
+
+enum { ACT_RPM = 0, ACT_FORCE = 1, ACT_SETPOINT = 2 };
+
+template <typename T> struct Rov6StepArgs {
+    Rov6Dev<T> P;
+    long n, ld;
+    T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
+    T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
+    T dt, h;
+    int n_sub, max_steps;
+    unsigned long long seed, env_id0;
+    int auto_reset, fixed_sp;
+};
+
+// dataToState, 6DoF.py:467-483 (iWp is always 0 in the reference)
+template <typename T>
+__device__ __forceinline__ void observe6(const Rov6Dev<T>& P, const T (&y)[12], const T (&path)[6], const T (&sp_ang)[3], T (&obs)[9]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        obs[k] = clampt((path[k] - y[k]) * P.inv_3L, T(-1), T(1));
+        obs[3 + k] = clampt((path[3 + k] - y[k]) * P.inv_3L, T(-1), T(1));
+        obs[6 + k] = clampt(angle_error(sp_ang[k], y[3 + k]) * P.inv_ang, T(-1), T(1));
+    }
+}
+
+// Random branch of reset().  The reference's own line raises (6DoF.py:497,
+// shapes (2,3)-(2,)); defined here as the 3-component analogue of 3DoF.py:423:
+// path = (U^(2x3) - 0.5) * 10, targetOrientation = U^3 * 2 pi.
+template <typename T>
+__device__ __forceinline__ void draw_reset6(unsigned long long seed, unsigned long long env, uint32_t episode, T (&path)[6], T (&orient)[3]) {
+    const uint4 a = Philox::draw(seed, env, episode, 0u, 0u);
+    const uint4 b = Philox::draw(seed, env, episode, 0u, 1u);
+    const uint4 c = Philox::draw(seed, env, episode, 0u, 2u);
+    path[0] = (u01<T>(a.x) - T(0.5)) * T(10); path[1] = (u01<T>(a.y) - T(0.5)) * T(10);
+    path[2] = (u01<T>(a.z) - T(0.5)) * T(10); path[3] = (u01<T>(a.w) - T(0.5)) * T(10);
+    path[4] = (u01<T>(b.x) - T(0.5)) * T(10); path[5] = (u01<T>(b.y) - T(0.5)) * T(10);
+    orient[0] = u01<T>(b.z) * T(MVRL_TWO_PI); orient[1] = u01<T>(b.w) * T(MVRL_TWO_PI);
+    orient[2] = u01<T>(c.x) * T(MVRL_TWO_PI);
+}
+
+// episode statistics: [episodes, sum length, sum return, min return, max return, non-finite, -, -]
+__device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, double len, double ret, bool bad) {
+    const unsigned active = __activemask();
+    const unsigned dm = __ballot_sync(active, is_done);
+    const unsigned bm = __ballot_sync(active, bad);
+    if (dm == 0u && bm == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    if (dm) {
+        const double sl = warp_sum(is_done ? len : 0.0, active);
+        const double sr = warp_sum(is_done ? ret : 0.0, active);
+        const double mn = warp_min(is_done ? ret : 1.0e300, active);
+        const double mx = warp_max(is_done ? ret : -1.0e300, active);
+        if (lane == leader) {
+            atomicAdd(stats + 0, (double)__popc(dm));
+            atomicAdd(stats + 1, sl);
+            atomicAdd(stats + 2, sr);
+            atomic_min_double(stats + 3, mn);
+            atomic_max_double(stats + 4, mx);
+        }
+    }
+    if (bm && lane == leader) atomicAdd(stats + 5, (double)__popc(bm));
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused env step.  action -> (set-point) -> n_sub x RK4 in registers ->
+// wrap -> observation -> done -> reward -> auto-reset.
+// ---------------------------------------------------------------------------
+template <typename T, int MODE, bool SP, bool FAST>
+__global__ void __launch_bounds__(128)
+rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Rov6Dev<T>& P = a.P;
+    const long ld = a.ld;
+    constexpr bool EXACT = (sizeof(T) == 8);
+
+    T y[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) y[k] = a.state[k * ld + i];
+    const int istep = a.istep[i] + 1;
+
+    constexpr int NA = (MODE == ACT_RPM) ? 8 : 6;
+    T act[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) act[k] = a.action[k * ld + i];
+
+    T sp[6];
+    T e_old[6], e_int[6];
+    if constexpr (MODE == ACT_SETPOINT) {
+        if (a.fixed_sp) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sp[k] = a.setpoint[k * ld + i];
+        } else {  // 6DoF.py:545-552
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sp[k] = act[k] * P.act_pos + y[k];
+                sp[3 + k] = act[3 + k] * P.act_ang + y[3 + k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { e_old[k] = a.ctrl[k * ld + i]; e_int[k] = a.ctrl[(6 + k) * ld + i]; }
+    } else {
+#pragma unroll
+        for (int k = 3; k < 6; ++k) sp[k] = a.setpoint[k * ld + i];
+    }
+
+    T H[6];       // thruster wrench of the current evaluation
+    T gcf[6];     // generalisedControlForces of the last evaluation
+    T dem[8];     // allocated demand (N) of the last evaluation
+    if constexpr (MODE == ACT_RPM) {
+        T F[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) F[k] = thruster_force(P, act[k]);
+        thrust_wrench<T, SP>(P, F, H);  // rpm is held over the env step: hoisted out of RK4
+    } else if constexpr (MODE == ACT_FORCE) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gcf[k] = act[k];
+    }
+
+    // one derivative evaluation; dtc = t - tOld of the PID (0 or h/2 inside a step)
+    auto f = [&](const T (&s)[12], T (&k)[12], T dtc) {
+        const Trig6<T> g = trig6<T, FAST>(s[3], s[4], s[5]);
+        const T nu[6] = {s[6], s[7], s[8], s[9], s[10], s[11]};
+        if constexpr (MODE != ACT_RPM) {
+            if constexpr (MODE == ACT_SETPOINT) {
+                const T pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
+                pid6(P, e_old, e_int, sp, pose, dtc, gcf);
+            }
+            allocate_demand<T, SP>(P, g, gcf, dem);
+            T F[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) F[j] = demand_to_force<T, EXACT>(P, dem[j]);
+            thrust_wrench<T, SP>(P, F, H);
+        }
+        T ed[6], acc[6], rhs[6];
+        kinematics6<T, FAST>(g, nu, ed);
+        body_accel<T, SP>(P, g, nu, H, acc, rhs);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { k[j] = ed[j]; k[6 + j] = acc[j]; }
+    };
+
+    const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6);
+    for (int sub = 0; sub < a.n_sub; ++sub) {
+        T k[12], acc[12], yt[12];
+        f(y, k, T(0));
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { acc[j] = k[j]; yt[j] = y[j] + hh * k[j]; }
+        f(yt, k, hh);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { acc[j] += T(2) * k[j]; yt[j] = y[j] + hh * k[j]; }
+        f(yt, k, T(0));
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { acc[j] += T(2) * k[j]; yt[j] = y[j] + h * k[j]; }
+        f(yt, k, hh);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) y[j] += h6 * (acc[j] + k[j]);
+    }
+
+    // 6DoF.py:560
+#pragma unroll
+    for (int k = 3; k < 6; ++k) y[k] = pymod_pos(y[k], T(MVRL_TWO_PI));
+
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) bad = bad || !finite_t(y[k]);
+
+    T path[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) path[k] = a.path[k * ld + i];
+    const T spa[3] = {sp[3], sp[4], sp[5]};
+    T obs[9];
+    observe6(P, y, path, spa, obs);
+    const bool is_done = istep >= a.max_steps;  // 6DoF.py:569-571
+
+    if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
+        if constexpr (MODE == ACT_RPM) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = T(0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = act[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = gcf[k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, dem[k]);
+        }
+    }
+    if (a.stats != nullptr) stats_accumulate(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
+
+    int istep_out = istep;
+    if (is_done && a.auto_reset) {
+        if (a.term_obs != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = obs[k];
+        }
+        const uint32_t ep = a.episode[i] + 1u;
+        a.episode[i] = ep;
+        istep_out = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) y[k] = T(0);
+        if (!a.fixed_sp) {
+            T orient[3];
+            draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep, path, orient);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.path[k * ld + i] = path[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sp[k] = path[k]; sp[3 + k] = orient[k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.setpoint[k * ld + i] = sp[k];
+        }
+        if constexpr (MODE == ACT_SETPOINT) {  // fresh controller, 6DoF.py:37-41, 514
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { e_old[k] = T(0); e_int[k] = T(0); }
+            e_old[0] = Real<T>::nan();
+        }
+        const T spa2[3] = {sp[3], sp[4], sp[5]};
+        observe6(P, y, path, spa2, obs);
+    }
+
+#pragma unroll
+    for (int k = 0; k < 12; ++k) a.state[k * ld + i] = y[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.obs[k * ld + i] = obs[k];
+    a.reward[i] = T(0);  // 6DoF.py:575
+    a.done[i] = is_done ? 1 : 0;
+    a.istep[i] = istep_out;
+    if constexpr (MODE == ACT_SETPOINT) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            a.setpoint[k * ld + i] = sp[k];
+            a.ctrl[k * ld + i] = e_old[k];
+            a.ctrl[(6 + k) * ld + i] = e_int[k];
+        }
+        a.ctrl[12 * ld + i] = T(istep_out) * a.dt;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: one derivative evaluation per environment, with optional dump of RHS,
+// controller forces, rpm and the retComp columns.
+// ---------------------------------------------------------------------------
+template <typename T> struct Rov6DerivArgs {
+    Rov6Dev<T> P;
+    long n, ld;
+    const T* state; const T* act; const T* t; const T* setpoint; T* ctrl; T* dstate; T* aux;
+};
+
+template <typename T, int MODE, bool SP>
+__global__ void __launch_bounds__(128)
+rov6_derivs_kernel(const __grid_constant__ Rov6DerivArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Rov6Dev<T>& P = a.P;
+    const long ld = a.ld;
+    T s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = a.state[k * ld + i];
+    const Trig6<T> g = trig6<T, false>(s[3], s[4], s[5]);
+    const T nu[6] = {s[6], s[7], s[8], s[9], s[10], s[11]};
+    T gcf[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    T rpm[8];
+    T F[8], H[6];
+    if constexpr (MODE == ACT_RPM) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { rpm[k] = a.act[k * ld + i]; F[k] = thruster_force(P, rpm[k]); }
+    } else {
+        if constexpr (MODE == ACT_FORCE) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) gcf[k] = a.act[k * ld + i];
+        } else {
+            T e_old[6], e_int[6], sp[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                e_old[k] = a.ctrl[k * ld + i]; e_int[k] = a.ctrl[(6 + k) * ld + i]; sp[k] = a.setpoint[k * ld + i];
+            }
+            const T t = a.t[i];
+            const T dtc = t - a.ctrl[12 * ld + i];
+            const T pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
+            pid6(P, e_old, e_int, sp, pose, dtc, gcf);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { a.ctrl[k * ld + i] = e_old[k]; a.ctrl[(6 + k) * ld + i] = e_int[k]; }
+            a.ctrl[12 * ld + i] = t;
+        }
+        T dem[8];
+        allocate_demand<T, SP>(P, g, gcf, dem);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { rpm[k] = demand_to_rpm(P, dem[k]); F[k] = thruster_force(P, rpm[k]); }
+    }
+    thrust_wrench<T, SP>(P, F, H);
+    T ed[6], acc[6], rhs[6];
+    kinematics6<T, false>(g, nu, ed);
+    body_accel<T, SP>(P, g, nu, H, acc, rhs, a.aux ? a.aux + 20 * ld + i : nullptr, ld);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a.dstate[k * ld + i] = ed[k]; a.dstate[(6 + k) * ld + i] = acc[k]; }
+    if (a.aux != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { a.aux[k * ld + i] = rhs[k]; a.aux[(6 + k) * ld + i] = gcf[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.aux[(12 + k) * ld + i] = rpm[k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// reset (6DoF.py:485-529)
+// ---------------------------------------------------------------------------
+template <typename T> struct Rov6ResetArgs {
+    Rov6Dev<T> P;
+    long n, ld;
+    T* state; T* obs; int32_t* istep; T* setpoint; T* path; T* ctrl; const uint32_t* episode; T* aux;
+    const uint8_t* mask;
+    T init_sp[6];
+    int has_init_sp;
+    unsigned long long seed, env_id0;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+rov6_reset_kernel(const __grid_constant__ Rov6ResetArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (a.mask != nullptr && a.mask[i] == 0) return;
+    const long ld = a.ld;
+    T y[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { y[k] = T(0); a.state[k * ld + i] = T(0); }  // 6DoF.py:517-519
+    a.istep[i] = 0;
+    T path[6], sp[6];
+    if (a.has_init_sp) {  // 6DoF.py:502-511
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sp[k] = a.init_sp[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { path[k] = sp[k]; path[3 + k] = sp[k]; }
+    } else {
+        T orient[3];
+        const uint32_t ep = a.episode ? a.episode[i] : 0u;
+        draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep, path, orient);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sp[k] = path[k]; sp[3 + k] = orient[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a.path[k * ld + i] = path[k]; a.setpoint[k * ld + i] = sp[k]; }
+    if (a.ctrl != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 13; ++k) a.ctrl[k * ld + i] = T(0);
+        a.ctrl[i] = Real<T>::nan();
+    }
+    if (a.aux != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 14; ++k) a.aux[k * ld + i] = T(0);
+    }
+    const T spa[3] = {sp[3], sp[4], sp[5]};
+    T obs[9];
+    observe6(a.P, y, path, spa, obs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.obs[k * ld + i] = obs[k];
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone PID (6DoF.py:43-73)
+// ---------------------------------------------------------------------------
+template <typename T> struct Rov6PidArgs {
+    Rov6Dev<T> P;
+    long n, ld;
+    const T* pose; const T* t; const T* setpoint; T* ctrl; T* forces;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+rov6_pid_kernel(const __grid_constant__ Rov6PidArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const long ld = a.ld;
+    T e_old[6], e_int[6], sp[6], pose[6], out[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        e_old[k] = a.ctrl[k * ld + i]; e_int[k] = a.ctrl[(6 + k) * ld + i];
+        sp[k] = a.setpoint[k * ld + i]; pose[k] = a.pose[k * ld + i];
+    }
+    const T t = a.t[i];
+    pid6(a.P, e_old, e_int, sp, pose, t - a.ctrl[12 * ld + i], out);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a.ctrl[k * ld + i] = e_old[k]; a.ctrl[(6 + k) * ld + i] = e_int[k]; a.forces[k * ld + i] = out[k]; }
+    a.ctrl[12 * ld + i] = t;
+}
+
+}  // namespace mvrl

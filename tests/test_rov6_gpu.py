@@ -1,0 +1,266 @@
+"""GPU parity tests of the 6DoF path: CUDA kernels (through the C ABI) vs the
+numpy oracle and vs the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): derivatives 1e-10 relative in fp64;
+1000-step trajectories 1e-8 in fp64 and 1e-4 in fp32.  "Relative" is measured
+per environment against |ref| + max|ref| so that components which cancel to
+~0 do not blow the ratio up.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv, Rov6Constants, Rov6Derivs
+    from marinevehiclereinforcementlearning_b200 import resources as res
+
+DEV = "cuda"
+
+
+def rel_err(a, ref):
+    ref = np.asarray(ref)
+    scale = np.abs(ref) + np.abs(ref).max(axis=-1, keepdims=True)
+    return (np.abs(np.asarray(a) - ref) / np.maximum(scale, 1e-300)).max()
+
+
+def fm(x, dtype=torch.float64):
+    """[N, k] numpy -> feature-major [k, N] CUDA tensor."""
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x).T), dtype=dtype, device=DEV)
+
+
+def sample_states(rng, n):
+    s = np.empty((n, 12))
+    s[:, 0:3] = rng.uniform(-5, 5, (n, 3))
+    s[:, 3:6] = rng.uniform(-np.pi, np.pi, (n, 3))
+    s[:, 6:9] = rng.uniform(-2, 2, (n, 3))
+    s[:, 9:12] = rng.uniform(-5, 5, (n, 3))
+    return s
+
+
+# ------------------------------------------------------------------ K2 ------
+def test_derivs_rpm_fp64_vs_golden_and_oracle():
+    g = load_golden("rov6")
+    f = Rov6Derivs(dtype=torch.float64, action_mode="rpm")
+    d, aux = f(fm(g["rpm_states"]), fm(g["rpm_rpms"]), want_aux=True)
+    assert rel_err(d.T.cpu().numpy(), g["rpm_derivs"]) < 1e-10
+    aux = aux.T.cpu().numpy()
+    assert rel_err(aux[:, 0:6], g["rpm_RHS"]) < 1e-10
+    comp = aux[:, 20:50].reshape(-1, 5, 6).transpose(0, 2, 1)  # [N, 6, 5] like forceModel(retComp=True)
+    assert np.abs(comp - g["rpm_retComp"]).max() < 1e-9
+    # config 2: 1e5 random states, eta ~ U(-pi, pi), nu ~ U(-2,2) / U(-5,5)
+    rng = np.random.default_rng(11)
+    s = sample_states(rng, 100_000)
+    rpm = rng.uniform(-4000, 4000, (100_000, 8))
+    ref = o.derivs6_rpm(o.Rov6Params(), s, rpm)
+    got = f(fm(s), fm(rpm)).T.cpu().numpy()
+    assert rel_err(got, ref) < 1e-10
+
+
+def test_derivs_force_fp64():
+    g = load_golden("rov6")
+    f = Rov6Derivs(dtype=torch.float64, action_mode="force")
+    d, aux = f(fm(g["force_states"]), fm(g["force_forces"]), want_aux=True)
+    assert rel_err(d.T.cpu().numpy(), g["force_derivs"]) < 1e-10
+    assert np.abs(aux[12:20].T.cpu().numpy() - g["force_cv"]).max() < 1e-8
+    rng = np.random.default_rng(12)
+    s = sample_states(rng, 50_000)
+    frc = rng.uniform(-1, 1, (50_000, 6)) * np.array([50., 50., 50., 2., 2., 2.])
+    ref = o.derivs6_force(o.Rov6Params(), s, frc)
+    assert rel_err(f(fm(s), fm(frc)).T.cpu().numpy(), ref) < 1e-10
+
+
+def test_derivs_pid_sequences_fp64():
+    g = load_golden("rov6")
+    f = Rov6Derivs(dtype=torch.float64, action_mode="setpoint")
+    n_env, n_call = g["pid_t"].shape
+    ctrl = Rov6Derivs.new_ctrl(n_env)
+    sp = fm(g["pid_sp"])
+    for c in range(n_call):
+        d, aux = f(fm(g["pid_states"][:, c]), t=torch.as_tensor(g["pid_t"][:, c], device=DEV), setpoint=sp, ctrl=ctrl, want_aux=True)
+        assert rel_err(d.T.cpu().numpy(), g["pid_derivs"][:, c]) < 1e-9, c
+        assert np.abs(aux[6:12].T.cpu().numpy() - g["pid_gcf"][:, c]).max() < 1e-9, c
+        assert np.abs(aux[12:20].T.cpu().numpy() - g["pid_cv"][:, c]).max() < 1e-6, c
+        assert np.abs(ctrl[6:12].T.cpu().numpy() - g["pid_eint"][:, c]).max() < 1e-12, c
+
+
+def test_derivs_fp32_close_to_fp64():
+    rng = np.random.default_rng(13)
+    s = sample_states(rng, 20_000)
+    rpm = rng.uniform(-4000, 4000, (20_000, 8))
+    ref = o.derivs6_rpm(o.Rov6Params(), s, rpm)
+    got = Rov6Derivs(dtype=torch.float32, action_mode="rpm")(fm(s, torch.float32), fm(rpm, torch.float32)).T.cpu().numpy()
+    # avoid the 1/cos(theta) pole for the fp32 statement
+    ok = np.abs(np.cos(s[:, 4])) > 0.05
+    assert rel_err(got[ok], ref[ok]) < 2e-5
+
+
+def test_generic_kernel_matches_specialised():
+    c = Rov6Constants()
+    c.CG = np.array([1e-300, 0., 0.05])  # breaks the default-sparsity test, changes nothing numerically
+    g = load_golden("rov6")
+    fg = Rov6Derivs(consts=c, dtype=torch.float64, action_mode="rpm")
+    fs = Rov6Derivs(dtype=torch.float64, action_mode="rpm")
+    dg = fg(fm(g["rpm_states"]), fm(g["rpm_rpms"]))
+    ds = fs(fm(g["rpm_states"]), fm(g["rpm_rpms"]))
+    assert not fg._get_handle().specialised and fs._get_handle().specialised
+    assert rel_err(dg.T.cpu().numpy(), g["rpm_derivs"]) < 1e-10
+    assert rel_err(dg.T.cpu().numpy(), ds.T.cpu().numpy()) < 1e-13
+    # a genuinely different vehicle: off-axis CG, cross damping, inertia products, net buoyancy
+    p = o.Rov6Params(CG=np.array([0.01, -0.02, 0.05]), Yr=-0.3, Nv=-0.2, Kvv=-0.4, Zq=-0.1, Mw=0.2, m=11.0,
+                     I=np.array([[0.16, 0.01, -0.02], [0.01, 0.17, 0.005], [-0.02, 0.005, 0.18]]))
+    p.dispVol = 11.4 / 1000.
+    c = Rov6Constants()
+    c.CG, c.Yr, c.Nv, c.Kvv, c.Zq, c.Mw, c.m, c.I = p.CG, p.Yr, p.Nv, p.Kvv, p.Zq, p.Mw, p.m, p.I
+    got = Rov6Derivs(consts=c, dtype=torch.float64, action_mode="rpm")(fm(g["rpm_states"]), fm(g["rpm_rpms"]))
+    assert rel_err(got.T.cpu().numpy(), o.derivs6_rpm(p, g["rpm_states"], g["rpm_rpms"])) < 1e-10
+
+
+# ------------------------------------------------------------------ K1 ------
+def make_env(n, mode, dtype=torch.float64, **kw):
+    kw.setdefault("auto_reset", False)
+    kw.setdefault("maxSteps", 10 ** 9)
+    return BlueROV2Heavy6DoFVecEnv(n, action_mode=mode, dtype=dtype, device=DEV, **kw)
+
+
+def test_trajectory_1000_steps_fp64_vs_reference_golden():
+    t = load_golden("traj6")
+    env = make_env(4, "rpm", n_sub=int(t["n_sub"]), dt=float(t["dt"]))
+    env.reset(initialSetpoint=np.zeros(6))
+    worst = 0.0
+    for k in range(t["actions"].shape[0]):
+        env.step(torch.as_tensor(t["actions"][k], device=DEV))
+        worst = max(worst, np.abs(env.systemState.cpu().numpy() - t["traj"][k]).max())
+    assert worst < 1e-8, worst
+    envf = make_env(2, "force", n_sub=int(t["n_sub"]), dt=float(t["dt"]))
+    envf.reset(initialSetpoint=np.zeros(6))
+    worst = 0.0
+    for k in range(t["force_actions"].shape[0]):
+        envf.step(torch.as_tensor(t["force_actions"][k], device=DEV))
+        worst = max(worst, np.abs(envf.systemState.cpu().numpy() - t["force_traj"][k]).max())
+    assert worst < 1e-8, worst
+
+
+def test_trajectory_4096_envs_fp64_vs_oracle():
+    """BASELINE config 2 (4096 envs, fp64, nSub 8, U(-3500,3500) rpm from seed
+    1234), 250 steps here against the numpy oracle (the 1000-step statement at
+    this width is made against the C oracle in test_rov6_c_oracle_gpu.py)."""
+    n, steps = 4096, 250
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    env = make_env(n, "rpm")
+    env.reset(initialSetpoint=np.zeros(6))
+    ref = o.Rov6EnvOracle(n, mode=o.MODE_RPM, max_steps=10 ** 9)
+    ref.reset(initial_setpoint=np.zeros(6))
+    worst = 0.0
+    for k in range(steps):
+        a = (torch.rand((n, 8), generator=gen, dtype=torch.float64) * 2 - 1) * 3500.0
+        obs, rew, done, _ = env.step(a.to(DEV))
+        ro, rr, rd, _ = ref.step(a.numpy())
+        if k % 10 == 9 or k == steps - 1:
+            worst = max(worst, np.abs(env.systemState.cpu().numpy() - ref.state).max())
+            assert np.abs(obs.cpu().numpy() - ro).max() < 1e-8
+    assert worst < 1e-8, worst
+    assert float(rew.abs().max()) == 0.0 and not bool(done.any())
+
+
+def test_trajectory_fp32_within_1e4():
+    """fp32 kernel vs the fp64 oracle over 1000 steps (tolerance 1e-4 on the
+    state, angles compared modulo 2 pi)."""
+    t = load_golden("traj6")
+    for fast in (False, True):
+        env = make_env(4, "rpm", dtype=torch.float32, n_sub=int(t["n_sub"]), dt=float(t["dt"]), fast_math=fast)
+        env.reset(initialSetpoint=np.zeros(6))
+        worst = 0.0
+        for k in range(t["actions"].shape[0]):
+            env.step(torch.as_tensor(t["actions"][k], device=DEV, dtype=torch.float32))
+            d = env.systemState.cpu().numpy().astype(np.float64) - t["traj"][k]
+            d[:, 3:6] = (d[:, 3:6] + np.pi) % (2 * np.pi) - np.pi
+            scale = 1.0 + np.abs(t["traj"][k])
+            worst = max(worst, (np.abs(d) / scale).max())
+        print("fp32 fast=%s worst scaled error over 1000 steps: %.3e" % (fast, worst))
+        assert worst < (1e-4 if not fast else 1e-3), (fast, worst)
+
+
+def test_env_semantics_fixed_setpoint_vs_reference_env():
+    e6 = load_golden("env6")
+    env = make_env(1, "setpoint", maxSteps=60, record_aux=True)
+    obs = [env.reset(initialSetpoint=e6["fixed_sp"]).cpu().numpy()[0]]
+    hist = []
+    for k in range(60):
+        ob, r, d, _ = env.step(torch.zeros((1, 6), dtype=torch.float64, device=DEV))
+        obs.append(ob.cpu().numpy()[0])
+        hist.append(np.concatenate([[float(env.time[0])], env.systemState.cpu().numpy()[0], env._aux[:, 0].cpu().numpy(),
+                                    env.setPoint.cpu().numpy()[0]]))
+        assert bool(d[0]) == bool(e6["fixed_done"][k]) and float(r[0]) == 0.0
+    assert np.abs(np.array(obs) - e6["fixed_obs"]).max() < 1e-8
+    ref = e6["fixed_history"][1:]
+    got = np.array(hist)
+    assert np.abs(got[:, :13] - ref[:, :13]).max() < 1e-8          # t + 12 states
+    assert np.abs(got[:, 13:19] - ref[:, 13:19]).max() < 1e-5      # controller forces of the last stage
+    assert np.abs(got[:, 27:] - ref[:, 27:]).max() < 1e-12         # set-point
+
+
+def test_env_semantics_action_driven_vs_reference_env():
+    e6 = load_golden("env6")
+    env = make_env(1, "setpoint", maxSteps=40)
+    env.reset(initialSetpoint=np.append(e6["act_path"][0], e6["act_orient"]))
+    env._path[:, 0] = torch.as_tensor(e6["act_path"].reshape(-1), device=DEV)
+    env.fixedSp = False
+    for k in range(40):
+        ob, r, d, _ = env.step(torch.as_tensor(e6["act_actions"][k:k + 1], device=DEV))
+        assert np.abs(ob.cpu().numpy()[0] - e6["act_obs"][k + 1]).max() < 1e-7, k
+        assert np.abs(env.systemState.cpu().numpy()[0] - e6["act_history"][k + 1, 1:13]).max() < 1e-7, k
+        assert bool(d[0]) == bool(e6["act_done"][k])
+
+
+def test_auto_reset_and_sharding_bitwise():
+    """Auto-reset (terminal_observation, Philox draws) vs the oracle, and
+    N envs in one launch == two shards with env_id0 offsets, bitwise."""
+    n, steps = 512, 12
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-3500, 3500, (steps, n, 8))
+    full = make_env(n, "rpm", maxSteps=5, auto_reset=True, seed=99)
+    a = make_env(n // 2, "rpm", maxSteps=5, auto_reset=True, seed=99, env_id0=0)
+    b = make_env(n // 2, "rpm", maxSteps=5, auto_reset=True, seed=99, env_id0=n // 2)
+    ref = o.Rov6EnvOracle(n, mode=o.MODE_RPM, max_steps=5, auto_reset=True, seed=99)
+    o0 = full.reset().cpu().numpy()
+    a.reset(); b.reset()
+    r0 = ref.reset()
+    assert np.abs(o0 - r0).max() < 1e-12
+    for k in range(steps):
+        act = torch.as_tensor(acts[k], device=DEV)
+        obs, rew, done, info = full.step(act)
+        oa, _, da, _ = a.step(act[: n // 2])
+        ob, _, db, _ = b.step(act[n // 2:])
+        assert torch.equal(obs, torch.cat([oa, ob])) and torch.equal(done, torch.cat([da, db]))
+        assert torch.equal(full.systemState, torch.cat([a.systemState, b.systemState]))
+        ro, rr, rd, rinfo = ref.step(acts[k])
+        assert np.array_equal(done.cpu().numpy(), rd)
+        assert np.abs(obs.cpu().numpy() - ro).max() < 1e-9
+        if rd.any():
+            assert np.abs(info["terminal_observation"].cpu().numpy()[rd] - rinfo["terminal_observation"][rd]).max() < 1e-9
+            assert np.abs(full.path.cpu().numpy().reshape(n, 6) - ref.path).max() < 1e-12
+            assert (full.iStep == 0).all()
+    st = full.episode_stats()
+    assert st["episodes"] == n * (steps // 5) and st["mean_length"] == 5.0 and st["nonfinite"] == 0
+
+
+def test_resources_helpers():
+    r = load_golden("resources")
+    got = res.angleError(r["angle_pairs"][:, 0], r["angle_pairs"][:, 1])
+    assert np.abs(got - r["angle_err"]).max() < 1e-14
+    assert res.angleError(0.1, 6.2) == pytest.approx(0.1831853071795857, abs=1e-15)
+    assert np.signbit(res.angleError(1.0, 1.0)) and res.angleError(0.0, np.pi) == -np.pi
+    a = r["ct_angles"]
+    J6 = res.coordinateTransform(a[:, 0], a[:, 1], a[:, 2], dof=6)
+    assert np.abs(J6 - r["ct_J6"]).max() / np.abs(r["ct_J6"]).max() < 1e-12
+    # away from the clamped pole the agreement is at round-off level
+    ok = np.abs(np.cos(a[:, 1])) > 1e-3
+    assert np.abs(J6[ok] - r["ct_J6"][ok]).max() < 1e-12
+    assert np.abs(res.coordinateTransform(a[:, 0], a[:, 1], a[:, 2], dof=3) - r["ct_J3"]).max() < 1e-15
+    assert res.coordinateTransform(0.1, 0.2, 0.3, dof=6).shape == (6, 6)
+    assert res.coordinateTransform(0.1, 0.2, 0.3).shape == (3, 3)
