@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the batched BlueROV2 6DoF env step (BASELINE.json metric:
+"BlueROV2 6DoF env-steps/sec ... (1M envs); % of FP pipe peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config 3 of BASELINE.json): BlueROV2 Heavy 6DoF,
+fp32, 1 048 576 environments PER GPU (weak scaling: the path shards by
+environment with no data-path collective), direct thruster-rpm actions
+~U(-3500, 3500) (seed 1234 + rank), dt = 0.2 s as nSub = 8 fixed RK4 sub-steps,
+maxSteps = 250 with auto-reset.  One "step" = one launch of the fused step
+kernel over the whole batch.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's CPU implementation of the same path:
+the reference is pure Python (no compiled artefact can be built from it and
+/root/reference does not exist on the GPU box), so this arm runs the C port of
+it (oracle/mvrl_oracle.c, pinned to vectors produced by the unmodified
+reference) on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "BlueROV2 6DoF env-steps/sec"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 1 << 20
+N_SUB = 8
+DT = 0.2
+MAX_STEPS = 250
+# algorithmic work of one 6DoF env step, direct-rpm mode
+FLOP_PER_ENV_STEP = 1600 * N_SUB + 60          # FMA = 2, other fp ops = 1, libm calls not counted
+BYTES_PER_ENV_STEP_F32 = 177                   # state r/w, action r, obs/reward/done w, counter r/w
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def workload_name(envs):
+    return ("rov6_step fp32: BlueROV2 Heavy 6DoF, %d envs/GPU, rpm actions U(-3500,3500), dt=%.1f as nSub=%d RK4, "
+            "maxSteps=%d auto-reset" % (envs, DT, N_SUB, MAX_STEPS))
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample inside the timed region"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------
+def cpu_port_rate(n_envs, n_steps, threads=0, seed=1234):
+    """env-steps/s of the C port of the reference's step loop on the host."""
+    from oracle import c_oracle as c
+    from oracle import oracle_np as o
+    env = c.Rov6EnvC(n_envs, mode=o.MODE_RPM, max_steps=MAX_STEPS, n_sub=N_SUB, dt=DT, auto_reset=True, seed=seed, threads=threads)
+    env.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-3500.0, 3500.0, (4, n_envs, 8))
+    env.step(acts[0])  # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        env.step(acts[k % 4])
+    dt = time.perf_counter() - t0
+    used = threads if threads > 0 else c.load().orc_max_threads()
+    return n_envs * n_steps / dt, dt, used
+
+
+def python_port_rate(seconds=3.0):
+    """env-steps/s of the numpy restatement stepped ONE environment at a time -
+    the shape of the reference's own loop (per-env Python/numpy, one core)."""
+    from oracle import oracle_np as o
+    env = o.Rov6EnvOracle(1, mode=o.MODE_RPM, max_steps=10 ** 9, n_sub=N_SUB, dt=DT)
+    env.reset(initial_setpoint=np.zeros(6))
+    rng = np.random.default_rng(0)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        env.step(rng.uniform(-3500, 3500, (1, 8)))
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_envs = 32768
+    from oracle import c_oracle as c
+    from oracle import oracle_np as o
+    threads = c.load().orc_max_threads()
+    env = c.Rov6EnvC(n_envs, mode=o.MODE_RPM, max_steps=MAX_STEPS, n_sub=N_SUB, dt=DT, auto_reset=True, seed=1234)
+    env.reset()
+    rng = np.random.default_rng(1234)
+    acts = rng.uniform(-3500.0, 3500.0, (4, n_envs, 8))
+    for k in range(args.warmup):
+        env.step(acts[k % 4])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        env.step(acts[k % 4])
+    t_total = time.perf_counter() - t0
+    rates = [0] * args.steps
+    value = n_envs * args.steps / t_total
+    sample = "%d envs x 1 env step per bench step (nSub=%d RK4), all host threads" % (n_envs, N_SUB)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / len(rates), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(ENVS_PER_GPU), "l2": "n/a (CPU arm)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv, _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    env = BlueROV2Heavy6DoFVecEnv(n, action_mode="rpm", dtype=torch.float32, device=dev, dt=DT, maxSteps=MAX_STEPS, n_sub=N_SUB,
+                                  seed=1234, env_id0=rank * n, auto_reset=True, fast_math=bool(args.fast_math),
+                                  record_terminal_obs=False)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_act = 4  # rotating action batches: 4 x 32 MiB on top of 125 MB touched per step > 126 MB L2
+    acts = [(torch.rand((8, env.ld), generator=gen, device=dev, dtype=torch.float32) * 2 - 1) * 3500.0 for _ in range(n_act)]
+    # stagger episode phase like a long-running job: env i starts at iStep = i % maxSteps
+    env._istep.copy_((torch.arange(env.ld, device=dev) % MAX_STEPS).to(torch.int32))
+
+    def one_step(k):
+        env._bufs.action = acts[k % n_act].data_ptr()
+        env.step_async()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        one_step(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for k in range(args.steps):
+        one_step(k)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = world * n * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    stats = env.episode_stats(reset=True)  # K5; all-reduced over NCCL when world > 1 (off the timed path)
+
+    # ---- end to end through the public API with HOST buffers -----------------
+    h_act = [a[:, :n].T.contiguous().cpu().pin_memory() for a in acts[:2]]          # [N, 8] like a VecEnv caller
+    h_obs = torch.empty((n, 9), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    env._bufs.action = env._action.data_ptr()
+
+    def e2e_step(k):
+        obs, rew, done, _ = env.step(h_act[k % 2])          # H2D of [N, 8] + transpose into SoA + fused step
+        h_obs.copy_(obs, non_blocking=True)                  # D2H of obs / reward / done
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(env._done[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t[0])
+    h2d = n * 8 * 4
+    d2h = n * (9 * 4 + 4 + 1)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        fp32_peak = _lib.measure_fma_peak(_lib.F32, local_rank)   # K6, measured now on this GPU
+        fp64_peak = _lib.measure_fma_peak(_lib.F64, local_rank, iters=1024)
+        per_gpu_rate = n / (ms_per_step * 1e-3)
+        ach_tflops = per_gpu_rate * FLOP_PER_ENV_STEP / 1e12
+        ach_gbs = per_gpu_rate * BYTES_PER_ENV_STEP_F32 / 1e9
+        roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak,
+                    "traffic": None, "peak_source": "FP32 FMA-chain microbenchmark (mvrl_measure_fma_peak) run on this GPU in this process; "
+                    "nominal %.1f" % NOMINAL_FP32_TFLOPS, "fp64_peak_tflops": fp64_peak,
+                    "flop_per_env_step": FLOP_PER_ENV_STEP,
+                    "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                            "bytes_per_env_step": BYTES_PER_ENV_STEP_F32, "peak_source": peak_src}}
+        cpu = None
+        if not args.no_cpu:
+            rate, secs, used = cpu_port_rate(32768, args.cpu_steps)
+            cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
+                   "sample": "%d envs x %d env steps of the same workload, C port of the reference loop, %d threads, %.1f s" %
+                             (32768, args.cpu_steps, used, secs),
+                   "python_port_one_core": python_port_rate(2.0)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(n), "envs_per_gpu": n, "envs_total": n * world, "n_sub": N_SUB,
+                           "action_mode": "rpm", "fast_math": bool(args.fast_math), "parallelism": "env-sharded x%d, no collective on the step path" % world,
+                           "l2": "inputs larger than L2: ~125 MB touched per step + 4 rotating 32 MiB action batches"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "path": "BlueROV2Heavy6DoFVecEnv.step(pinned host [N,8] actions) -> pinned host obs/reward/done"},
+                "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--fast-math", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=100)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

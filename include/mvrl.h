@@ -175,6 +175,12 @@ MVRL_API int mvrl_angle_error(int dtype, int64_t n, const void* psi_d, const voi
 MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const void* angles /* T [3][ld] */, void* out,
                    mvrl_stream_t stream);
 
+/* ------------------------------------------------------------ calibration -- */
+/* K6: measured FMA throughput of the FP32 / FP64 pipe in TFLOP/s (2 flop per FMA,
+ * 8 independent chains per thread, 8 x 256 threads per SM).  Roofline denominator
+ * for the FP-pipe-bound step kernels; synchronises (measurement utility). */
+MVRL_API int mvrl_measure_fma_peak(int dtype, int device, int iters, double* tflops_out, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

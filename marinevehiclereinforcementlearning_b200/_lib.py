@@ -69,6 +69,7 @@ PROTOTYPES = {
     "mvrl_coordinate_transform": (_int, [_int, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mvrl_angle_error": (_int, [_int, _i64, _vp, _vp, _vp, _vp]),
     "mvrl_body_axes": (_int, [_int, _i64, _i64, _vp, _vp, _vp]),
+    "mvrl_measure_fma_peak": (_int, [_int, _int, _int, C.POINTER(_d), C.POINTER(_d)]),
 }
 
 _lib = None
@@ -136,3 +137,11 @@ def torch_dtype_code(dtype):
     if dtype == torch.float64:
         return F64
     raise ValueError("dtype must be torch.float32 or torch.float64, got %r" % (dtype,))
+
+
+def measure_fma_peak(dtype_code, device=0, iters=4096):
+    """K6: measured FMA-pipe throughput in TFLOP/s (roofline denominator)."""
+    require_cuda()
+    tf, ms = C.c_double(), C.c_double()
+    check(load().mvrl_measure_fma_peak(dtype_code, device, iters, C.byref(tf), C.byref(ms)))
+    return tf.value

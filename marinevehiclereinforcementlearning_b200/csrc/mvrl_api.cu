@@ -440,3 +440,56 @@ extern "C" MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const v
     else return mvrl_fail(MVRL_EINVAL, "bad dtype");
     return check_launch("body_axes");
 }
+
+// ---------------------------------------------------------------------------
+// K6: FP-pipe peak calibration (roofline denominator).  Every thread runs
+// CHAINS independent dependent-FMA chains; 2 flop per FMA.  This entry point
+// is a measurement utility: it allocates a scratch buffer and synchronises.
+// ---------------------------------------------------------------------------
+template <typename T, int CHAINS>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T x[CHAINS];
+#pragma unroll
+    for (int j = 0; j < CHAINS; ++j) x[j] = T(threadIdx.x + j) * T(1e-3);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int j = 0; j < CHAINS; ++j) x[j] = x[j] * a + b;
+        }
+    }
+    T s = T(0);
+#pragma unroll
+    for (int j = 0; j < CHAINS; ++j) s += x[j];
+    out[(long)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" MVRL_API int mvrl_measure_fma_peak(int dtype, int device, int iters, double* tflops_out, double* ms_out) {
+    if (!tflops_out || iters < 1) return mvrl_fail(MVRL_EINVAL, "mvrl_measure_fma_peak: bad argument");
+    MVRL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MVRL_CUDA(cudaGetDeviceProperties(&prop, device));
+    constexpr int CH = 8;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void* buf = nullptr;
+    MVRL_CUDA(cudaMalloc(&buf, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    MVRL_CUDA(cudaEventCreate(&e0));
+    MVRL_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {  // first reps warm the clocks up; keep the best
+        MVRL_CUDA(cudaEventRecord(e0, 0));
+        if (dtype == MVRL_F64) fma_peak_kernel<double, CH><<<blocks, threads>>>((double*)buf, iters, 0.999999, 1e-7);
+        else fma_peak_kernel<float, CH><<<blocks, threads>>>((float*)buf, iters, 0.999999f, 1e-7f);
+        MVRL_CUDA(cudaEventRecord(e1, 0));
+        MVRL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        MVRL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    const double flops = 2.0 * CH * 8.0 * (double)iters * (double)blocks * threads;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return check_launch("fma_peak");
+}

@@ -109,11 +109,12 @@ class Rov6EnvC:
         self.done = np.zeros(n, dtype=np.uint8)
         self.term_obs = np.zeros((n, 9))
         self.aux = np.zeros((n, 14))
+        self.mincos = np.ones(n)  # running min |cos(theta)| over all RK4 stages (conditioning diagnostic)
         return self.obs.copy()
 
     def step(self, action):
         action = np.ascontiguousarray(action, dtype=np.float64)
         self.lib.orc_rov6_step(C.byref(self.ps), C.byref(self.cfg), C.c_long(self.n), _p(self.state), _p(action),
                                _p(self.set_point), _p(self.path), self.ctrl, _p(self.i_step), _p(self.time), _p(self.episode),
-                               _p(self.obs), _p(self.done), _p(self.term_obs), _p(self.aux))
+                               _p(self.obs), _p(self.done), _p(self.term_obs), _p(self.aux), _p(self.mincos))
         return self.obs, np.zeros(self.n), self.done.astype(bool), {"terminal_observation": self.term_obs}

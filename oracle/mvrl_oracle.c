@@ -284,10 +284,12 @@ typedef struct OrcRov6Env {
 
 /* One env step for n environments, 6DoF.py:531-594 with the integrator fixed to RK4 x n_sub.
  * state [n][12], action [n][8|6], setpoint [n][6], path [n][6], ctrl [n], istep [n], time [n],
- * episode [n] -> obs [n][9], done [n], term_obs [n][9] (nullable), aux [n][14] (nullable). */
+ * episode [n] -> obs [n][9], done [n], term_obs [n][9] (nullable), aux [n][14] (nullable).
+ * mincos [n] (nullable, in/out): running minimum of |cos(theta)| over every RK4 stage - a conditioning
+ * diagnostic for the tests (distance from the 1/cos(theta) pole of J2), not part of the algorithm. */
 void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* state, const double* action, double* setpoint,
                    double* path, OrcPid6* ctrl, int32_t* istep, double* time, uint32_t* episode, double* obs, uint8_t* done,
-                   double* term_obs, double* aux) {
+                   double* term_obs, double* aux, double* mincos) {
     const int na = e->mode == 0 ? 8 : 6;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(e->threads > 0 ? e->threads : omp_get_max_threads())
@@ -317,6 +319,10 @@ void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* 
             derivs6(p, e->mode, t + 0.5 * h, yt, act, sp, c, k3, gcf, cv);
             for (int k = 0; k < 12; ++k) yt[k] = y[k] + h * k3[k];
             derivs6(p, e->mode, t + h, yt, act, sp, c, k4, gcf, cv);
+            if (mincos) {
+                const double th[4] = {y[4], y[4] + 0.5 * h * k1[4], y[4] + 0.5 * h * k2[4], yt[4]};
+                for (int q = 0; q < 4; ++q) mincos[i] = fmin(mincos[i], fabs(cos(th[q])));
+            }
             for (int k = 0; k < 12; ++k) y[k] = y[k] + (h / 6.0) * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
         }
         for (int k = 3; k < 6; ++k) y[k] = pymod(y[k], TWO_PI); /* 6DoF.py:560 */
