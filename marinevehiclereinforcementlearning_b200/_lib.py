@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmvrl.so")
+# MVRL_LIB selects an alternative build of the same sources (kernel-tuning experiments)
+LIB_PATH = os.environ.get("MVRL_LIB") or os.path.join(_PKG_DIR, "libmvrl.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 F32, F64 = 0, 1

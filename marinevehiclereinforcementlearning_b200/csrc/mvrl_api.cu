@@ -163,6 +163,10 @@ template <typename T> static void to_dev(const MvrlRov6Params& p, Rov6Dev<T>& d)
     }
     d.inv_3L = T(1. / (p.Length * 3.)); d.act_pos = T(2. * p.Length);
     d.act_ang = T(45. / 180. * pi); d.inv_ang = T(1. / (45. / 180. * pi));
+    d.mX = T(p.m - p.Xudot); d.mY = T(p.m - p.Yvdot); d.mZ = T(p.m - p.Zwdot); d.mzg = T(p.m * p.CG[2]);
+    d.cVW = T(p.Yvdot - p.Zwdot); d.cUW = T(p.Zwdot - p.Xudot); d.cUV = T(p.Xudot - p.Yvdot);
+    d.cQR = T(p.I[8] - p.I[4] + p.Mqdot - p.Nrdot); d.cPR = T(p.I[0] - p.I[8] + p.Nrdot - p.Kpdot);
+    d.cPQ = T(p.I[4] - p.I[0] + p.Kpdot - p.Mqdot);
     d.thrusters_on = p.disable_thrusters ? 0 : 1;
 }
 
@@ -228,9 +232,19 @@ static int check_launch(const char* what) {
 // ---------------------------------------------------------------------------
 // step
 // ---------------------------------------------------------------------------
+#ifndef MVRL_STAGE_UNROLL_F32
+#define MVRL_STAGE_UNROLL_F32 4
+#endif
+#ifndef MVRL_STAGE_UNROLL_F64
+#define MVRL_STAGE_UNROLL_F64 4
+#endif
+#define MVRL_STAGE_UNROLL(T) (sizeof(T) == 4 ? MVRL_STAGE_UNROLL_F32 : MVRL_STAGE_UNROLL_F64)
+
 template <typename T, int MODE, bool SP, bool FAST>
 static void launch_step(const Rov6StepArgs<T>& a, cudaStream_t s) {
-    rov6_step_kernel<T, MODE, SP, FAST><<<grid_for(a.n, 128), 128, 0, s>>>(a);
+    // the four RK4 stages are unrolled: measured faster than the rolled loop (r1 profile notes)
+    constexpr int UNROLL = MVRL_STAGE_UNROLL(T);
+    rov6_step_kernel<T, MODE, SP, FAST, UNROLL><<<grid_for(a.n, MVRL_STEP_BLOCK), MVRL_STEP_BLOCK, 0, s>>>(a);
 }
 template <typename T, bool FAST>
 static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, cudaStream_t s) {

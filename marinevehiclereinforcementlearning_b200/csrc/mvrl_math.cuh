@@ -28,6 +28,8 @@ template <> struct Real<double> {
 template <typename T> __device__ __forceinline__ T tabs(T x) { return x < T(0) ? -x : x; }
 template <> __device__ __forceinline__ float tabs<float>(float x) { return fabsf(x); }
 template <> __device__ __forceinline__ double tabs<double>(double x) { return fabs(x); }
+__device__ __forceinline__ float fmaf_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fmaf_t(double a, double b, double c) { return fma(a, b, c); }
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ T clampt(T x, T lo, T hi) { return tmax(lo, tmin(hi, x)); }

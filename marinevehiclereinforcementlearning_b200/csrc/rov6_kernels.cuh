@@ -74,8 +74,15 @@ __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, do
 // K1: fused env step.  action -> (set-point) -> n_sub x RK4 in registers ->
 // wrap -> observation -> done -> reward -> auto-reset.
 // ---------------------------------------------------------------------------
-template <typename T, int MODE, bool SP, bool FAST>
-__global__ void __launch_bounds__(128)
+#ifndef MVRL_STEP_BLOCK
+#define MVRL_STEP_BLOCK 128
+#endif
+#ifndef MVRL_STEP_MINB
+#define MVRL_STEP_MINB 1
+#endif
+
+template <typename T, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
+__global__ void __launch_bounds__(MVRL_STEP_BLOCK, (sizeof(T) == 4 ? MVRL_STEP_MINB : 1))
 rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -148,28 +155,36 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
         for (int j = 0; j < 6; ++j) { k[j] = ed[j]; k[6 + j] = acc[j]; }
     };
 
-    const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6);
+    // classic RK4, y' = y + h/6 (k1 + 2 k2 + 2 k3 + k4), accumulated as
+    // y' = (((y + h/6 k1) + h/3 k2) + h/3 k3) + h/6 k4: one FMA per state and stage.
+    const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6), h3 = a.h / T(3);
     for (int sub = 0; sub < a.n_sub; ++sub) {
         T k[12], acc[12], yt[12];
-        f(y, k, T(0));
 #pragma unroll
-        for (int j = 0; j < 12; ++j) { acc[j] = k[j]; yt[j] = y[j] + hh * k[j]; }
-        f(yt, k, hh);
+        for (int j = 0; j < 12; ++j) { acc[j] = y[j]; yt[j] = y[j]; }
+#pragma unroll STAGE_UNROLL
+        for (int st = 0; st < 4; ++st) {
+            f(yt, k, (st & 1) ? hh : T(0));
+            const T wk = (st == 0 || st == 3) ? h6 : h3;
+            const T ck = (st == 2) ? h : hh;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) { acc[j] += T(2) * k[j]; yt[j] = y[j] + hh * k[j]; }
-        f(yt, k, T(0));
+            for (int j = 0; j < 12; ++j) {
+                acc[j] = fmaf_t(wk, k[j], acc[j]);
+                if (st < 3) yt[j] = fmaf_t(ck, k[j], y[j]);
+            }
+        }
 #pragma unroll
-        for (int j = 0; j < 12; ++j) { acc[j] += T(2) * k[j]; yt[j] = y[j] + h * k[j]; }
-        f(yt, k, hh);
-#pragma unroll
-        for (int j = 0; j < 12; ++j) y[j] += h6 * (acc[j] + k[j]);
+        for (int j = 0; j < 12; ++j) y[j] = acc[j];
     }
 
+    bool bad = false;
+    if constexpr (sizeof(T) == 4 && !FAST) {  // outside the exact range of the fp32 sin/cos reduction
+#pragma unroll
+        for (int k = 3; k < 6; ++k) bad = bad || tabs(y[k]) > T(MVRL_SINCOS_F32_MAX_ARG);
+    }
     // 6DoF.py:560
 #pragma unroll
     for (int k = 3; k < 6; ++k) y[k] = pymod_pos(y[k], T(MVRL_TWO_PI));
-
-    bool bad = false;
 #pragma unroll
     for (int k = 0; k < 12; ++k) bad = bad || !finite_t(y[k]);
 

@@ -26,23 +26,59 @@ template <typename T> struct Rov6Dev {
     T f_max, f_db;            // thruster force at rpm_max / at the deadband edge
     T pKp[6], pKi[6], pKd[6], pWind[6], pMax[6];
     T inv_3L, act_pos, act_ang, inv_ang;  // 1/(3 Length), 2 Length, pi/4, 4/pi
+    // Crb + Ca folded for the default sparsity (see body_accel): effective masses
+    // m - Xudot.., m*zg, and the differences that multiply the velocity products
+    T mX, mY, mZ, mzg, cVW, cUW, cUV, cQR, cPR, cPQ;
     int thrusters_on;
 };
 
 template <typename T> struct Trig6 { T sph, cph, sth, cth, sps, cps; };
 
+// fp32 sin/cos without libm's branches: Cody-Waite reduction by pi/2 (three
+// FMAs, exact for |x| < 2^16) + the minimax polynomials of the Cephes sinf /
+// cosf kernels (|r| <= pi/4, ~1 ulp) + branch-free quadrant fix-up.  Angles are
+// wrapped to [0, 2 pi) every env step, so |x| stays far below 2^16; the step
+// kernel flags any environment whose unwrapped angle leaves that range in its
+// non-finite/out-of-range counter instead of paying a branch per evaluation.
+#define MVRL_SINCOS_F32_MAX_ARG 65536.0f
+
+__device__ __forceinline__ void sincos_f32(float x, float* sn, float* cs) {
+    const float j = fmaf(x, 0.636619772367581343f, 12582912.0f);   // round(x * 2/pi) in the low mantissa bits
+    const int q = __float_as_int(j);
+    const float k = j - 12582912.0f;
+    float r = fmaf(k, -1.5703125f, x);
+    r = fmaf(k, -4.837512969970703125e-4f, r);
+    r = fmaf(k, -7.549789954891882e-8f, r);
+    const float z = r * r;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float s0 = fmaf(ps * z, r, r);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    const float c0 = fmaf(pc * z, z, fmaf(z, -0.5f, 1.0f));
+    const bool swap = (q & 1) != 0;
+    const float s1 = swap ? c0 : s0;
+    const float c1 = swap ? s0 : c0;
+    *sn = __int_as_float(__float_as_int(s1) ^ ((q & 2) << 30));
+    *cs = __int_as_float(__float_as_int(c1) ^ (((q + 1) & 2) << 30));
+}
+
+template <typename T, bool FAST>
+__device__ __forceinline__ void sincos_t(T x, T* s, T* c) {
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (FAST) { *s = __sinf(x); *c = __cosf(x); }   // MUFU.SIN / MUFU.COS
+        else sincos_f32(x, s, c);
+    } else {
+        Real<T>::sincos(x, s, c);
+    }
+}
+
 template <typename T, bool FAST>
 __device__ __forceinline__ Trig6<T> trig6(T phi, T theta, T psi) {
     Trig6<T> g;
-    if constexpr (FAST && sizeof(T) == 4) {
-        g.sph = __sinf(phi);   g.cph = __cosf(phi);
-        g.sth = __sinf(theta); g.cth = __cosf(theta);
-        g.sps = __sinf(psi);   g.cps = __cosf(psi);
-    } else {
-        Real<T>::sincos(phi, &g.sph, &g.cph);
-        Real<T>::sincos(theta, &g.sth, &g.cth);
-        Real<T>::sincos(psi, &g.sps, &g.cps);
-    }
+    sincos_t<T, FAST>(phi, &g.sph, &g.cph);
+    sincos_t<T, FAST>(theta, &g.sth, &g.cth);
+    sincos_t<T, FAST>(psi, &g.sps, &g.cps);
     return g;
 }
 
@@ -151,6 +187,30 @@ template <typename T, bool SP>
 __device__ __forceinline__ void body_accel(const Rov6Dev<T>& P, const Trig6<T>& g, const T (&nu)[6], const T (&H)[6],
                                            T (&acc)[6], T (&rhs)[6], T* comp = nullptr, long comp_ld = 0) {
     const T u = nu[0], v = nu[1], w = nu[2], p = nu[3], q = nu[4], r = nu[5];
+    if constexpr (SP) {
+        if (comp == nullptr) {
+            // Default sparsity, no component dump: Crb v + Ca v folded analytically
+            // (xg = yg = 0, diagonal inertia; the m w v - m v w pairs of 6DoF.py:313-331
+            // cancel identically) and every product accumulated straight into RHS by FMA.
+            const T pr = p * r, qr = q * r;
+            rhs[0] = fmaf_t(fmaf_t(P.Xuu, tabs(u), P.Xu), u, fmaf_t(-P.mzg, pr, fmaf_t(-P.mZ, w * q, fmaf_t(P.mY, v * r, H[0]))));
+            rhs[1] = fmaf_t(fmaf_t(P.Yvv, tabs(v), P.Yv), v, fmaf_t(-P.mzg, qr, fmaf_t(-P.mX, u * r, fmaf_t(P.mZ, w * p, H[1]))));
+            rhs[2] = fmaf_t(fmaf_t(P.Zww, tabs(w), P.Zw), w, fmaf_t(P.mzg, fmaf_t(q, q, p * p), fmaf_t(P.mX, u * q, fmaf_t(-P.mY, v * p, H[2]))));
+            rhs[3] = fmaf_t(fmaf_t(P.Kpp, tabs(p), P.Kp), p,
+                            fmaf_t(-P.gz, g.cth * g.sph, fmaf_t(-P.cQR, qr, fmaf_t(-P.cVW, v * w, fmaf_t(-P.mzg, fmaf_t(-r, u, p * w), H[3])))));
+            rhs[4] = fmaf_t(fmaf_t(P.Mqq, tabs(q), P.Mq), q,
+                            fmaf_t(P.Mww * tabs(w), w,
+                                   fmaf_t(-P.gz, g.sth, fmaf_t(-P.cPR, pr, fmaf_t(-P.cUW, u * w, fmaf_t(-P.mzg, fmaf_t(-r, v, q * w), H[4]))))));
+            rhs[5] = fmaf_t(fmaf_t(P.Nrr, tabs(r), P.Nr), r, fmaf_t(-P.cPQ, p * q, fmaf_t(-P.cUV, u * v, H[5])));
+            acc[0] = fmaf_t(P.Minv[0][4], rhs[4], P.Minv[0][0] * rhs[0]);
+            acc[1] = fmaf_t(P.Minv[1][3], rhs[3], P.Minv[1][1] * rhs[1]);
+            acc[2] = P.Minv[2][2] * rhs[2];
+            acc[3] = fmaf_t(P.Minv[3][1], rhs[1], P.Minv[3][3] * rhs[3]);
+            acc[4] = fmaf_t(P.Minv[4][0], rhs[0], P.Minv[4][4] * rhs[4]);
+            acc[5] = P.Minv[5][5] * rhs[5];
+            return;
+        }
+    }
     const T m = P.m;
     T crb[6], ca[6], dv[6], G[6];
 
@@ -266,21 +326,33 @@ __device__ __forceinline__ void body_accel(const Rov6Dev<T>& P, const Trig6<T>& 
 template <typename T, bool FAST>
 __device__ __forceinline__ void kinematics6(const Trig6<T>& g, const T (&nu)[6], T (&ed)[6]) {
     const T u = nu[0], v = nu[1], w = nu[2], p = nu[3], q = nu[4], r = nu[5];
-    const T ss = g.sth * g.sph;  // sin(theta) sin(phi)
-    ed[0] = g.cps * g.cth * u + (-g.sps * g.cph + g.cps * ss) * v + (g.sps * g.sph + g.cps * ss) * w;
-    ed[1] = g.sps * g.cth * u + (g.cps * g.cph + g.sps * ss) * v + (-g.cps * g.sph + g.sps * g.sth * g.cph) * w;
-    ed[2] = -g.sth * u + g.cth * g.sph * v + g.cth * g.cph * w;
-    T den = g.cth;
-    const T ad = tabs(den);
-    if (ad < T(1e-12)) den = T(1e-6);
-    else if (ad < T(1e-6)) den = T(1e-6) * sgn(den);
+    // J1 v factored through psi: x' = c(psi) A1 - s(psi) B, y' = s(psi) A2 + c(psi) B with
+    // A1 = c(th) u + s(th)s(ph) (v + w)   <- the reference's J1[0][2] (sin(phi), not cos(phi))
+    // A2 = c(th) u + s(th)s(ph) v + s(th)c(ph) w,  B = c(ph) v - s(ph) w
+    const T ss = g.sth * g.sph, sc = g.sth * g.cph, cu = g.cth * u;
+    const T A1 = fmaf_t(ss, v + w, cu);
+    const T A2 = fmaf_t(sc, w, fmaf_t(ss, v, cu));
+    const T B = fmaf_t(g.cph, v, -(g.sph * w));
+    ed[0] = fmaf_t(g.cps, A1, -(g.sps * B));
+    ed[1] = fmaf_t(g.sps, A2, g.cps * B);
+    ed[2] = fmaf_t(g.cth, fmaf_t(g.sph, v, g.cph * w), -(g.sth * u));
+    // resources.py:116-120, branch-free: |c| < 1e-12 -> 1e-6, |c| < 1e-6 -> 1e-6 sign(c)
+    const T ad = tabs(g.cth);
+    const T tiny = ad < T(1e-12) ? T(1e-6) : copysign(T(1e-6), g.cth);
+    const T den = ad < T(1e-6) ? tiny : g.cth;
     T inv;
-    if constexpr (FAST && sizeof(T) == 4) inv = __frcp_rn(den);
-    else inv = T(1) / den;
-    const T a = g.sph * q + g.cph * r;  // shared by rows 0 and 2 of J2
-    ed[3] = p + g.sth * inv * a;
-    ed[4] = g.cph * q - g.sph * r;
+    if constexpr (sizeof(T) == 4) {
+        // |den| >= 1e-6 after the clamp: MUFU.RCP needs no special-case path; one Newton step
+        // brings it to <= 1 ulp in the accurate mode.
+        inv = __fdividef(1.0f, den);
+        if constexpr (!FAST) inv = fmaf(inv, fmaf(-den, inv, 1.0f), inv);
+    } else {
+        inv = T(1) / den;
+    }
+    const T a = fmaf_t(g.sph, q, g.cph * r);  // shared by rows 0 and 2 of J2
     ed[5] = inv * a;
+    ed[3] = fmaf_t(g.sth, ed[5], p);
+    ed[4] = fmaf_t(g.cph, q, -(g.sph * r));
 }
 
 // BlueROV2Heavy6DoF_PID_controller.computeControlForces, 6DoF.py:43-73.
