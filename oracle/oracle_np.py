@@ -539,3 +539,417 @@ class Rov6EnvOracle:
     def history_row(self):
         """The 33 columns the reference appends per step, 6DoF.py:578-580."""
         return np.concatenate([self.time[:, None], self.state, self.gcf, self.cv, self.set_point], axis=1)
+
+
+# ==========================================================================
+# 3DoF model (3DoF.py:25-296) and env (3DoF.py:375-514)
+# ==========================================================================
+@dataclass
+class Rov3Params:
+    """3DoF.py:39-112.  Attribute names are the reference's."""
+    rho_f: float = 1000.
+    m: float = 11.4
+    Length: float = 0.457
+    Width: float = 0.338
+    CB: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    CG: np.ndarray = field(default_factory=lambda: np.array([0., 0., 0.02]))
+    I: np.ndarray = field(default_factory=lambda: np.diag([0.16, 0.16, 0.16]))
+    Xudot: float = -5.5
+    Yvdot: float = -12.7
+    Nrdot: float = -0.12
+    Yrdot: float = 0.
+    Nvdot: float = 0.
+    Xuu: float = -18.18
+    Yvv: float = -21.66
+    Yrr: float = 0.
+    Ypp: float = 0.
+    Nvv: float = 0.
+    Nrr: float = -1.55
+    Npp: float = 0.
+    Xu: float = -4.03
+    Yv: float = -6.22
+    Yr: float = 0.
+    Yp: float = 0.
+    Nv: float = 0.
+    Nr: float = -0.07
+    Np: float = 0.
+    D_thruster: float = 0.1
+    alphaThruster: float = 45. / 180. * np.pi
+    l_x: float = 0.156
+    l_y: float = 0.111
+
+    def __post_init__(self):
+        self.dispVol = self.m / self.rho_f
+        self.Kt_thruster = 40. / (1000. * (3500. / 60.) ** 2. * self.D_thruster ** 4.)
+        A = np.array([[1., 1., -1., -1.], [1., -1., 1., -1.], [1., 1., 1., 1.]])
+        A[0, :] = A[0, :] * np.cos(self.alphaThruster)
+        A[1, :] = A[1, :] * np.sin(self.alphaThruster)
+        A[2, :] = A[2, :] * np.sin(self.alphaThruster) * self.Length / 2.  # allocation uses Length/2 arms (3DoF.py:111)
+        self.A = A
+        self.Ainv = np.linalg.pinv(A)
+
+    def mass_matrix(self):
+        """3DoF.py:198-206."""
+        m, xg, yg = self.m, self.CG[0], self.CG[1]
+        Mrb = np.array([[m, 0., -m * yg], [0., m, m * xg], [-m * yg, m * xg, self.I[2, 2]]])
+        return Mrb + -1. * np.diag([self.Xudot, self.Yvdot, self.Nrdot])
+
+
+PID3_WINDUP = np.array([2., 2., 90. / 180. * np.pi])
+PID3_KP = np.array([20., 20., 20.])
+PID3_KI = np.array([0.1, 0.1, 0.1])
+PID3_KD = np.array([5., 5., 0.5])
+PID3_MAX = np.array([150., 150., 100.])
+
+
+def pid3_new_state(n):
+    """3DoF.py:33-35."""
+    return {"eOld": np.zeros((n, 3)), "has_old": np.zeros(n, dtype=bool), "eInt": np.zeros((n, 3)), "tOld": np.zeros(n)}
+
+
+def pid3_control(ctrl, set_point, pose, t):
+    """3DoF.py:141-157 (mutates ``ctrl`` on every call)."""
+    t = np.broadcast_to(np.asarray(t, dtype=float), pose.shape[:1])
+    e = np.stack([set_point[:, 0] - pose[:, 0], set_point[:, 1] - pose[:, 1], angle_error(set_point[:, 2], pose[:, 2])], axis=1)
+    e_old = np.where(ctrl["has_old"][:, None], ctrl["eOld"], e)
+    dtc = t - ctrl["tOld"]
+    dedt = (e - e_old) / np.maximum(1e-9, dtc)[:, None]
+    e_int = ctrl["eInt"] + 0.5 * (e_old + e) * dtc[:, None]
+    e_int = np.where(np.abs(e) > PID3_WINDUP, 0., e_int)
+    u = PID3_KP * e + PID3_KD * dedt + PID3_KI * e_int
+    u = np.maximum(-PID3_MAX, np.minimum(PID3_MAX, u))
+    ctrl["eOld"], ctrl["eInt"], ctrl["tOld"] = e, e_int, t.copy()
+    ctrl["has_old"] = np.ones_like(ctrl["has_old"])
+    return u
+
+
+def thruster_model3(p, u, rpm):
+    """3DoF.py:114-126 -> (Fthruster, Xthruster) with the jet-velocity drag augment."""
+    F = p.rho_f * (rpm / 60.) ** 2. * np.sign(rpm) * p.D_thruster ** 4. * p.Kt_thruster
+    u_jet = np.sqrt(np.abs(F) / (0.5 * p.rho_f * np.pi * p.D_thruster ** 2))
+    den = np.maximum(1e-5, u_jet)
+    d_cd = 0.56599 * np.exp(-7.60891 * np.abs(u) / den) + 0.05654 * np.exp(-0.89679 * np.abs(u) / den)
+    X = d_cd * -0.5 * p.rho_f * np.abs(u) * u * p.dispVol ** (2. / 3.)
+    return F, X
+
+
+def allocate_thrust3(p, psi, control_values):
+    """3DoF.py:159-168 -> (generalisedControlForces in the body frame, rpm)."""
+    Xd = control_values[:, 0] * np.cos(psi) + control_values[:, 1] * np.sin(psi)
+    Yd = -control_values[:, 0] * np.sin(psi) + control_values[:, 1] * np.cos(psi)
+    gcf = np.stack([Xd, Yd, control_values[:, 2]], axis=1)
+    cv = gcf @ p.Ainv.T
+    cv = np.sign(cv) * np.sqrt(np.abs(cv) / (p.rho_f * p.D_thruster ** 4. * p.Kt_thruster)) * 60.
+    return gcf, cv
+
+
+def derivs3_rpm(p, state, rpm):
+    """3DoF.py:170-296 from the limited-rpm stage on (rpm given: FP, AP, FS, AS)."""
+    state = np.atleast_2d(np.asarray(state, dtype=float))
+    rpm = np.atleast_2d(np.asarray(rpm, dtype=float))
+    psi, u, v, r = state[:, 2], state[:, 3], state[:, 4], state[:, 5]
+    m, xg, yg = p.m, p.CG[0], p.CG[1]
+    lim = limit_rpm(rpm)
+    F, X = thruster_model3(p, u[:, None], lim)
+    ca, sa = np.cos(p.alphaThruster), np.sin(p.alphaThruster)
+    Xh = X[:, 0] + X[:, 1] + X[:, 2] + X[:, 3] + (F[:, 0] + F[:, 1] - F[:, 2] - F[:, 3]) * ca
+    Yh = (F[:, 0] - F[:, 1] + F[:, 2] - F[:, 3]) * sa
+    Nh = np.sqrt(p.l_x ** 2. + p.l_y ** 2.) * (F[:, 0] + F[:, 1] + F[:, 2] + F[:, 3])  # true moment arms, 3DoF.py:263
+    crb = np.stack([-m * (xg * r + v) * r, -m * (yg * r - u) * r, m * (xg * r + v) * u + m * (yg * r - u) * v], axis=1)
+    cav = np.stack([p.Yvdot * v * r, -p.Xudot * u * r, -p.Yvdot * v * u + p.Xudot * u * v], axis=1)
+    dv = -np.stack([(p.Xu + p.Xuu * np.abs(u)) * u,
+                    (p.Yv + p.Yvv * np.abs(v)) * v + (p.Yr + p.Yrr * np.abs(r)) * r,
+                    (p.Nv + p.Nvv * np.abs(v)) * v + (p.Nr + p.Nrr * np.abs(r)) * r], axis=1)
+    RHS = -crb - (cav + dv) + np.stack([Xh, Yh, Nh], axis=1)
+    acc = np.linalg.solve(p.mass_matrix(), RHS.T).T
+    vel = np.stack([np.cos(psi) * u - np.sin(psi) * v, np.sin(psi) * u + np.cos(psi) * v, r], axis=1)
+    return np.concatenate([vel, acc], axis=1)
+
+
+def derivs3_pid(p, t, state, ctrl, set_point, return_aux=False):
+    """BlueROV2Heavy3DoF.derivs, 3DoF.py:128-296 (mutates ``ctrl``)."""
+    state = np.atleast_2d(np.asarray(state, dtype=float))
+    control_values = pid3_control(ctrl, set_point, state[:, 0:3], t)
+    gcf, cv = allocate_thrust3(p, state[:, 2], control_values)
+    d = derivs3_rpm(p, state, cv)
+    return (d, gcf, cv) if return_aux else d
+
+
+class Rov3EnvOracle:
+    """Vectorised BlueROV2Heavy3DoFEnv (3DoF.py:375-514) with RK4 x n_sub.
+    mode 0: action = 4 rpm (build addition, stateless); 2: the reference's
+    set-point semantics."""
+
+    def __init__(self, n, params=None, dt=0.2, max_steps=250, n_sub=8, mode=MODE_PID, seed=0, auto_reset=False, env_id0=0):
+        self.n, self.p = n, (params or Rov3Params())
+        self.dt, self.max_steps, self.n_sub, self.mode, self.seed = dt, max_steps, n_sub, mode, seed
+        self.auto_reset = auto_reset
+        self.env_ids = np.arange(env_id0, env_id0 + n, dtype=np.uint64)
+        self.episode = np.zeros(n, dtype=np.uint64)
+        self.fixed_sp = False
+
+    def _draw(self, idx):
+        """3DoF.py:423-424: path = (U^(2x2) - 0.5) * 10, heading = U * 2 pi (Philox instead of np.random)."""
+        u = philox_uniform(self.seed, self.env_ids[idx], self.episode[idx], 5)
+        return (u[:, :4] - 0.5) * 10., u[:, 4] * TWO_PI
+
+    def reset(self, initial_setpoint=None):
+        n = self.n
+        self.i_step = np.zeros(n, dtype=np.int64)
+        self.time = np.zeros(n)
+        self.state = np.zeros((n, 6))
+        self.path = np.zeros((n, 4))
+        if initial_setpoint is None:
+            path, head = self._draw(np.arange(n))
+            self.path[:] = path
+            self.set_point = np.concatenate([path[:, :2], head[:, None]], axis=1)
+            self.fixed_sp = False
+        else:
+            sp = np.broadcast_to(np.asarray(initial_setpoint, dtype=float), (n, 3)).copy()
+            self.path[:, :2] = sp[:, :2]
+            self.path[:, 2:] = sp[:, :2]
+            self.set_point = sp
+            self.fixed_sp = True
+        self.ctrl = pid3_new_state(n)
+        self.gcf = np.zeros((n, 3))
+        self.cv = np.zeros((n, 4))
+        return self.observe()
+
+    def _reset_rows(self, idx):
+        self.episode[idx] += np.uint64(1)
+        self.i_step[idx] = 0
+        self.time[idx] = 0.
+        self.state[idx] = 0.
+        if not self.fixed_sp:
+            path, head = self._draw(idx)
+            self.path[idx] = path
+            self.set_point[idx] = np.concatenate([path[:, :2], head[:, None]], axis=1)
+        for k in ("eOld", "eInt"):
+            self.ctrl[k][idx] = 0.
+        self.ctrl["has_old"][idx] = False
+        self.ctrl["tOld"][idx] = 0.
+        self.gcf[idx] = 0.
+        self.cv[idx] = 0.
+
+    def observe(self):
+        """3DoF.py:397-409."""
+        s, L3 = self.state, self.p.Length * 3.
+        obs = np.concatenate([(self.path[:, 0:2] - s[:, 0:2]) / L3, (self.path[:, 2:4] - s[:, 0:2]) / L3,
+                              (angle_error(self.set_point[:, 2], s[:, 2]) / (45. / 180. * np.pi))[:, None]], axis=1)
+        return np.clip(obs, -1., 1.)
+
+    def step(self, action):
+        action = np.atleast_2d(np.asarray(action, dtype=float))
+        self.i_step += 1
+        self.time = self.time + self.dt
+        if self.mode == MODE_PID and not self.fixed_sp:  # 3DoF.py:469-472
+            L2 = 2. * self.p.Length
+            self.set_point = action * np.array([L2, L2, 45. / 180. * np.pi]) + self.state[:, :3]
+        if self.mode == MODE_RPM:
+            def f(t, y):
+                self.cv = action
+                return derivs3_rpm(self.p, y, action)
+        else:
+            def f(t, y):
+                d, self.gcf, self.cv = derivs3_pid(self.p, t, y, self.ctrl, self.set_point, return_aux=True)
+                return d
+        y = rk4_advance(f, self.time - self.dt, self.state, self.dt, self.n_sub)
+        y[:, 2] = np.mod(y[:, 2], TWO_PI)  # 3DoF.py:480
+        self.state = y
+        obs = self.observe()
+        done = self.i_step >= self.max_steps
+        info = {}
+        if self.auto_reset and done.any():
+            info["terminal_observation"] = obs.copy()
+            self._reset_rows(np.nonzero(done)[0])
+            obs = self.observe()
+        return obs, np.zeros(self.n), done, info
+
+    def history_row(self):
+        """17 columns, 3DoF.py:498-507."""
+        return np.concatenate([self.time[:, None], self.state, self.gcf, self.cv, self.set_point], axis=1)
+
+
+# ==========================================================================
+# legacy: ReconstructedFlow.scale / interp (legacy/flowGenerator.py:53-136)
+# ==========================================================================
+class FlowOracle:
+    """Holds ``baseFlowData`` [Nt, Ny, Nx, 3] (u/Uinf, v/Uinf, Cp) on a uniform
+    grid and reproduces ``scale`` and ``interp``.  The SPOD reconstruction of
+    ``__init__`` (legacy/flowGenerator.py:15-23) needs blobs that are absent
+    from the reference checkout; callers supply the base field."""
+
+    def __init__(self, base_field, base_dx=0.005, base_dy=0.005, base_dt=0.002):
+        self.baseFlowData = np.asarray(base_field, dtype=float)
+        self.baseDx, self.baseDy, self.baseDt = float(base_dx), float(base_dy), float(base_dt)
+        self.scale(1., 1., 1.)
+
+    def scale(self, sizeScale, velocityScale, turbScale, translate=(0, 0)):
+        """legacy/flowGenerator.py:53-95.  ``translate`` only moves the plotting
+        coordinates; ``interp`` ignores it (bug-compatible)."""
+        self.dx = self.baseDx * sizeScale
+        self.dy = self.baseDy * sizeScale
+        f = self.baseFlowData.copy()
+        f[..., 0] *= velocityScale
+        f[..., 1] *= velocityScale
+        f[..., 0] = (f[..., 0] - velocityScale) * turbScale + velocityScale
+        f[..., 1] = (f[..., 1] - 0.) * turbScale
+        f[..., 2] /= max(1e-6, (velocityScale * turbScale) ** 2.)
+        self.flowData = f
+        self.dt = self.baseDt * sizeScale / max(1e-6, velocityScale)
+        self.time = np.array([i * self.dt for i in range(f.shape[0])])
+
+    def interp(self, time, xy):
+        """legacy/flowGenerator.py:97-136, vectorised: time [N], xy [N, 2] -> [N, 3].
+        Indices are clamped to the grid, weights are NOT (extrapolation)."""
+        time = np.atleast_1d(np.asarray(time, dtype=float))
+        xy = np.atleast_2d(np.asarray(xy, dtype=float))
+        nt, ny, nx, _ = self.flowData.shape
+        tt, xx, yy = time / self.dt, xy[:, 0] / self.dx, xy[:, 1] / self.dy
+        kk = np.minimum(nt - 2, np.maximum(0, np.floor(tt).astype(np.int64)))
+        ii = np.minimum(nx - 2, np.maximum(0, np.floor(xx).astype(np.int64)))
+        jj = np.minimum(ny - 2, np.maximum(0, np.floor(yy).astype(np.int64)))
+        wt, wx, wy = tt - kk, xx - ii, yy - jj
+        f = self.flowData
+        res = np.zeros((time.shape[0], f.shape[3]))
+        for dk, ct in ((0, 1. - wt), (1, wt)):
+            c00, c01 = f[kk + dk, jj, ii], f[kk + dk, jj, ii + 1]
+            c10, c11 = f[kk + dk, jj + 1, ii], f[kk + dk, jj + 1, ii + 1]
+            row0 = c00 * (1. - wx)[:, None] + c01 * wx[:, None]       # F[jj, ii:ii+2] . xx
+            row1 = c10 * (1. - wx)[:, None] + c11 * wx[:, None]
+            res += ((1. - wy)[:, None] * row0 + wy[:, None] * row1) * ct[:, None]
+        return res
+
+
+# ==========================================================================
+# legacy: AuvEnv (legacy/verySimpleAuv.py:76-410)
+# ==========================================================================
+class AuvEnvOracle:
+    """Vectorised AuvEnv.  Random draws of ``reset`` come from Philox in the
+    reference's order (8 coefficient multipliers, 3 actuation multipliers,
+    position x/y, heading, headingTarget, flow time offset -
+    legacy/verySimpleAuv.py:222-245); ``set_initial`` installs values drawn by
+    the reference's own RNG for the golden-vector tests."""
+
+    def __init__(self, n, flow, dt=0.02, noiseMagCoeffs=0.0, noiseMagActuation=0.0, stopOnBoundsExceeded=True,
+                 max_steps=250, seed=0, auto_reset=False, env_id0=0):
+        self.n, self.flow, self.dt = n, flow, dt
+        self.noiseMagCoeffs, self.noiseMagActuation = noiseMagCoeffs, noiseMagActuation
+        self.stop_on_bounds, self.max_steps = stopOnBoundsExceeded, max_steps
+        self.seed, self.auto_reset = seed, auto_reset
+        self.env_ids = np.arange(env_id0, env_id0 + n, dtype=np.uint64)
+        self.episode = np.zeros(n, dtype=np.uint64)
+        # legacy/verySimpleAuv.py:110-127
+        self.xMinMax, self.yMinMax = [-1, 1], [-1, 1]
+        self.m, self.Izz = 11.4, 0.16
+        self.Xuu, self.Yvv, self.Nrr = -18.18 * 2.21, -21.66 * 4.87, -1.55
+        self.Xu, self.Yv, self.Nr = -4.03 * 2.21, -6.22 * 4.87, -0.07
+        self.maxForce, self.maxMoment = 150., 20.
+
+    def _draw(self, idx, apply_noise=True):
+        u = philox_uniform(self.seed, self.env_ids[idx], self.episode[idx], 16)
+        mults = np.ones((len(idx), 11))
+        if apply_noise:
+            mults[:, :8] = 1. + self.noiseMagCoeffs / 2. - u[:, :8] * self.noiseMagCoeffs
+            mults[:, 8:] = 1. + self.noiseMagActuation / 2. - u[:, 8:11] * self.noiseMagActuation
+        pos = (u[:, 11:13] - 0.5) * 0.5 * np.array([self.xMinMax[1] - self.xMinMax[0], self.yMinMax[1] - self.yMinMax[0]])
+        heading, target = u[:, 13] * TWO_PI, u[:, 14] * TWO_PI
+        offset = u[:, 15] * self.flow.time[self.flow.time.shape[0] // 4]
+        return mults, pos, heading, target, offset
+
+    def _install(self, idx, mults, pos, heading, target, offset):
+        self.mults[idx], self.position[idx], self.heading[idx] = mults, pos, heading
+        self.heading_target[idx], self.t_offset[idx] = target, offset
+        self.velocities[idx] = 0.
+        self.time[idx] = 0.
+        self.i_step[idx] = 0
+        self.recent[idx] = 0.
+        self.n_recent[idx] = 0
+        # first dataToState after reset initialises herr_o / perr_o (legacy/verySimpleAuv.py:158-160)
+        self.perr_o[idx] = -self.position[idx]
+        self.herr_o[idx] = angle_error(self.heading_target[idx], self.heading[idx])
+
+    def reset(self, applyNoise=True):
+        n = self.n
+        self.mults, self.position, self.heading = np.ones((n, 11)), np.zeros((n, 2)), np.zeros(n)
+        self.heading_target, self.t_offset = np.zeros(n), np.zeros(n)
+        self.velocities, self.time, self.i_step = np.zeros((n, 3)), np.zeros(n), np.zeros(n, dtype=np.int64)
+        self.recent, self.n_recent = np.zeros((n, 10, 3)), np.zeros(n, dtype=np.int64)
+        self.perr_o, self.herr_o = np.zeros((n, 2)), np.zeros(n)
+        idx = np.arange(n)
+        self._install(idx, *self._draw(idx, applyNoise))
+        return self.observe()
+
+    def set_initial(self, mults, pos, heading, target, offset):
+        self._install(np.arange(self.n), np.asarray(mults, float), np.asarray(pos, float), np.asarray(heading, float),
+                      np.asarray(target, float), np.asarray(offset, float))
+        return self.observe()
+
+    def observe(self):
+        """dataToState V3, legacy/verySimpleAuv.py:147-214 (uses herr_o / perr_o of the previous call)."""
+        perr = -self.position
+        herr = angle_error(self.heading_target, self.heading)
+        c = lambda x: np.minimum(1., np.maximum(-1., x))
+        return np.stack([c(perr[:, 0]), c(perr[:, 1]), c(herr / (45. / 180. * np.pi)), c(herr - self.herr_o),
+                         c(perr[:, 0] - self.perr_o[:, 0]), c(perr[:, 1] - self.perr_o[:, 1]),
+                         c(self.velocities[:, 0]), c(self.velocities[:, 1]), c(self.velocities[:, 2]),
+                         np.zeros(self.n), np.zeros(self.n)], axis=1)
+
+    def step(self, action):
+        """legacy/verySimpleAuv.py:264-410."""
+        action = np.atleast_2d(np.asarray(action, dtype=float))
+        n = self.n
+        self.i_step += 1
+        self.time = self.time + self.dt
+        done = self.i_step >= self.max_steps
+        self.recent = np.concatenate([action[:, None, :], self.recent[:, :9]], axis=1)  # deque.appendleft, maxlen 10
+        self.n_recent = np.minimum(10, self.n_recent + 1)
+        mm = self.mults
+        Fset = action[:, :2] * self.maxForce * mm[:, 8:10]
+        Nset = action[:, 2] * self.maxMoment * mm[:, 10]
+        c, s = np.cos(self.heading), np.sin(self.heading)
+        vel_current = self.flow.interp(self.time + self.t_offset, self.position)[:, :2]
+        d = self.velocities[:, :2] - vel_current
+        vr0, vr1 = c * d[:, 0] + s * d[:, 1], -s * d[:, 0] + c * d[:, 1]          # inverse of the planar rotation
+        r = self.velocities[:, 2]
+        Fh = np.stack([(self.Xu * mm[:, 5] + self.Xuu * mm[:, 2] * np.abs(vr0)) * vr0,
+                       (self.Yv * mm[:, 6] + self.Yvv * mm[:, 3] * np.abs(vr1)) * vr1,
+                       (self.Nr * mm[:, 7] + self.Nrr * mm[:, 4] * np.abs(r)) * r], axis=1)
+        Fh = np.stack([c * Fh[:, 0] - s * Fh[:, 1], s * Fh[:, 0] + c * Fh[:, 1], Fh[:, 2]], axis=1)
+        acc = np.stack([(Fh[:, 0] + Fset[:, 0]) / (self.m * mm[:, 0]), (Fh[:, 1] + Fset[:, 1]) / (self.m * mm[:, 0]),
+                        (Fh[:, 2] + Nset) / (self.Izz * mm[:, 1])], axis=1)
+        # explicit Euler; position advances with the OLD velocity (legacy/verySimpleAuv.py:321-326)
+        position = self.position + self.velocities[:, :2] * self.dt
+        heading = np.mod(self.heading + self.velocities[:, 2] * self.dt, TWO_PI)
+        velocities = self.velocities + acc * self.dt
+        self.position, self.heading, self.velocities = position, heading, velocities
+        obs = self.observe()
+        bonus = np.zeros(n)
+        out_x = (position[:, 0] < self.xMinMax[0]) | (position[:, 0] > self.xMinMax[1])
+        out_y = (position[:, 1] < self.yMinMax[0]) | (position[:, 1] > self.yMinMax[1])
+        bonus += -100. * out_x + -100. * out_y
+        if self.stop_on_bounds:
+            done = done | out_x | out_y
+        perr = -position
+        herr = angle_error(self.heading_target, heading)
+        self.herr_o, self.perr_o = herr, perr
+        # population std of the <= 10 most recent actions, mean over the 3 components (:353-355)
+        cnt = self.n_recent[:, None, None]
+        valid = (np.arange(10)[None, :, None] < cnt)
+        mean = (self.recent * valid).sum(axis=1) / self.n_recent[:, None]
+        var = (((self.recent - mean[:, None, :]) ** 2.) * valid).sum(axis=1) / self.n_recent[:, None]
+        rms_ac = np.sqrt(var).mean(axis=1)
+        herr_deg = np.abs(herr / np.pi * 180.)
+        terms = np.stack([np.exp(-5. * np.sqrt(perr[:, 0] ** 2 + perr[:, 1] ** 2)),
+                          np.where(np.abs(herr) < np.pi / 2., np.exp(-0.1 * herr_deg), -np.exp(-0.1 * (180. - herr_deg))),
+                          np.exp(-0.6 * rms_ac), -0.1 * np.sum(action ** 2., axis=1) / 3., bonus], axis=1)
+        reward = terms.sum(axis=1)
+        self.last = {"Fhydro": Fh, "Fset": Fset, "Nset": Nset, "vel_current": vel_current, "rmsAc": rms_ac, "terms": terms}
+        info = {}
+        if self.auto_reset and done.any():
+            idx = np.nonzero(done)[0]
+            info["terminal_observation"] = obs.copy()
+            self.episode[idx] += np.uint64(1)
+            self._install(idx, *self._draw(idx, True))
+            obs = self.observe()
+        return obs, reward, done, info
