@@ -166,6 +166,13 @@ MVRL_API int mvrl_rov6_reset(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6B
 MVRL_API int mvrl_rov6_pid(MvrlRov6* h, int64_t n, int64_t ld, const void* pose, const void* t, const void* setpoint,
                   void* ctrl, void* forces, mvrl_stream_t stream);
 
+/* BlueROV2Heavy6DoF.thrusterModel(rpm) (6DoF.py:233-236): rpm T [n] -> F T [n]; no saturation/deadband */
+MVRL_API int mvrl_rov6_thruster_model(MvrlRov6* h, int64_t n, const void* rpm, void* F, mvrl_stream_t stream);
+/* globalToVehicle (to_vehicle = 1) / vehicleToGlobal (0), 6DoF.py:244-251:
+ * axes T [9][ld] (iHat jHat kHat from mvrl_body_axes), v T [3][ld] -> out T [3][ld] */
+MVRL_API int mvrl_frame_rotate(int dtype, int64_t n, int64_t ld, const void* axes, const void* v, void* out, int to_vehicle,
+                               mvrl_stream_t stream);
+
 /* ------------------------------------------------------- resources.py -- */
 /* J(phi,theta,psi): out T [dof*dof][ld] row-major entries, dof = 3 or 6 */
 MVRL_API int mvrl_coordinate_transform(int dtype, int dof, int64_t n, int64_t ld, const void* phi, const void* theta,
@@ -174,6 +181,112 @@ MVRL_API int mvrl_angle_error(int dtype, int64_t n, const void* psi_d, const voi
 /* iHat jHat kHat: out T [9][ld] */
 MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const void* angles /* T [3][ld] */, void* out,
                    mvrl_stream_t stream);
+
+/* ---------------------------------------------------------------- 3DoF -- */
+
+/* Constants of BlueROV2Heavy3DoF (dynamicsModel_BlueROV2_Heavy_3DoF.py:39-112). */
+typedef struct MvrlRov3Params {
+    double rho_f, m, Length, dispVol;
+    double xg, yg, Izz;                       /* CG[0], CG[1], I[2,2] */
+    double Xudot, Yvdot, Nrdot;
+    double Xu, Yv, Yr, Nv, Nr;                /* 3DoF.py:225-229 */
+    double Xuu, Yvv, Yrr, Nvv, Nrr;           /* 3DoF.py:231-239 */
+    double D_thruster, thrust_coef;           /* thrust_coef = rho_f D^4 Kt */
+    double alphaThruster, l_x, l_y;           /* 3DoF.py:89-91 */
+    double rpm_max, rpm_deadband;
+    double M[9], Minv[9];                     /* 3DoF.py:198-206 and its inverse */
+    double Ainv[12];                          /* 4x3 pseudo-inverse, row-major (3DoF.py:104-112) */
+    double pid_Kp[3], pid_Ki[3], pid_Kd[3], pid_windup[3], pid_max[3]; /* 3DoF.py:142-154 */
+} MvrlRov3Params;
+
+/* action_mode: MVRL_ACT_RPM (4 thruster rpm FP AP FS AS; stateless) or
+ * MVRL_ACT_SETPOINT (the reference's semantics, 3DoF.py:466-472). */
+typedef MvrlRov6Config MvrlRov3Config;
+
+typedef struct MvrlRov3Buffers {
+    void* state;        /* T [6][ld] x y psi u v r                         in/out */
+    void* action;       /* T [4|3][ld]                                     in     */
+    void* obs;          /* T [5][ld]  3DoF.py:397-409                      out    */
+    void* reward;       /* T [ld]                                          out    */
+    uint8_t* done;      /* [ld]                                            out    */
+    int32_t* istep;     /* [ld]                                            in/out */
+    void* setpoint;     /* T [3][ld]                                       in/out */
+    void* path;         /* T [4][ld]  path[0,:], path[1,:]                 in (out on reset) */
+    void* ctrl;         /* T [7][ld]  eOld(3) eInt(3) tOld; eOld[0]=NaN <=> None */
+    uint32_t* episode;  /* [ld] */
+    void* terminal_obs; /* T [5][ld], nullable */
+    void* aux;          /* T [7][ld] generalisedControlForces(3), controlVector(4); nullable */
+    double* ep_stats;   /* [8], nullable */
+} MvrlRov3Buffers;
+
+typedef struct MvrlRov3 MvrlRov3;
+
+MVRL_API int mvrl_rov3_default_params(MvrlRov3Params* out);
+MVRL_API int mvrl_rov3_create(MvrlRov3** out, const MvrlRov3Params* params, const MvrlRov3Config* cfg);
+MVRL_API int mvrl_rov3_destroy(MvrlRov3* h);
+/* derivs: act = rpm T [4][ld] (RPM mode) or t/setpoint/ctrl (SETPOINT mode); aux nullable T [7][ld] */
+MVRL_API int mvrl_rov3_derivs(MvrlRov3* h, int64_t n, int64_t ld, const void* state, const void* act, const void* t,
+                              const void* setpoint, void* ctrl, void* dstate, void* aux, mvrl_stream_t stream);
+MVRL_API int mvrl_rov3_step(MvrlRov3* h, int64_t n, int64_t ld, const MvrlRov3Buffers* b, mvrl_stream_t stream);
+MVRL_API int mvrl_rov3_reset(MvrlRov3* h, int64_t n, int64_t ld, const MvrlRov3Buffers* b, const uint8_t* mask,
+                             const double* initial_setpoint_host /* 3 or NULL */, mvrl_stream_t stream);
+/* BlueROV2Heavy3DoF.thrusterModel(u, v, rpm) -> (Fthruster, Xthruster), 3DoF.py:114-126 */
+MVRL_API int mvrl_rov3_thruster_model(MvrlRov3* h, int64_t n, const void* u, const void* rpm, void* F, void* X,
+                                      mvrl_stream_t stream);
+
+/* -------------------------------------------------------------- legacy -- */
+
+/* AuvEnv constants, tag_00.../verySimpleAuv.py:110-132 */
+typedef struct MvrlAuvParams {
+    double m, Izz, Xuu, Yvv, Nrr, Xu, Yv, Nr, maxForce, maxMoment;
+    double xMin, xMax, yMin, yMax;
+    double noiseMagCoeffs, noiseMagActuation;
+} MvrlAuvParams;
+
+typedef struct MvrlAuvConfig {
+    int dtype, max_steps;
+    double dt;                 /* 0.02 */
+    uint64_t seed, env_id0;
+    int auto_reset, stop_on_bounds, apply_noise, device;
+} MvrlAuvConfig;
+
+typedef struct MvrlAuvBuffers {
+    void* state;        /* T [6][ld] x y psi u v r                                  in/out */
+    void* action;       /* T [3][ld]                                                in     */
+    void* obs;          /* T [11][ld] dataToState V3, verySimpleAuv.py:201-212      out    */
+    void* reward;       /* T [ld]                                                   out    */
+    uint8_t* done;      /* [ld]                                                     out    */
+    int32_t* istep;     /* [ld]                                                     in/out */
+    void* mults;        /* T [11][ld] m I Xuu Yvv Nrr Xu Yv Nr Xact Yact Nact       in (out on reset) */
+    void* target;       /* T [2][ld] headingTarget, flowDataTimeOffset              in (out on reset) */
+    void* err_o;        /* T [3][ld] perr_o x, perr_o y, herr_o                     in/out */
+    void* recent;       /* T [30][ld] the 10 most recent actions (ring)             in/out */
+    void* ep_return;    /* T [ld] running episode return                            in/out */
+    uint32_t* episode;  /* [ld] */
+    void* terminal_obs; /* T [11][ld], nullable */
+    void* aux;          /* T [14][ld] Fx Fy N Fx_set Fy_set N_set u_current v_current rmsAc r0..r4
+                           (log columns of verySimpleAuv.py:389-401); nullable */
+    double* ep_stats;   /* [8], nullable */
+} MvrlAuvBuffers;
+
+typedef struct MvrlAuv MvrlAuv;
+
+MVRL_API int mvrl_auv_default_params(MvrlAuvParams* out);
+MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* params, const MvrlAuvConfig* cfg);
+MVRL_API int mvrl_auv_destroy(MvrlAuv* h);
+/* Scaled flow field the env gathers from: device T [nt][ny][nx][nc], nc = 2 (u, v) or 3; the
+ * caller keeps it alive.  dx, dy, dt are the SCALED spacings (flowGenerator.py:77-78, 94). */
+MVRL_API int mvrl_auv_set_flow(MvrlAuv* h, const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt);
+MVRL_API int mvrl_auv_step(MvrlAuv* h, int64_t n, int64_t ld, const MvrlAuvBuffers* b, mvrl_stream_t stream);
+/* init nullable T [4][ld]: x, y, heading, headingTarget (fixedInitialValues) */
+MVRL_API int mvrl_auv_reset(MvrlAuv* h, int64_t n, int64_t ld, const MvrlAuvBuffers* b, const uint8_t* mask, const void* init,
+                            mvrl_stream_t stream);
+/* ReconstructedFlow.interp (flowGenerator.py:97-136): t T [n], xy T [2][ld] -> out T [nc][ld] */
+MVRL_API int mvrl_flow_interp(int dtype, const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt,
+                              int64_t n, int64_t ld, const void* t, const void* xy, void* out, mvrl_stream_t stream);
+/* ReconstructedFlow.scale on the values (flowGenerator.py:80-90): base T [cells][3] -> out T [cells][nc_out] */
+MVRL_API int mvrl_flow_scale(int dtype, int64_t cells, const void* base, void* out, int nc_out, double velocityScale,
+                             double turbScale, mvrl_stream_t stream);
 
 /* ------------------------------------------------------------ calibration -- */
 /* K6: measured FMA throughput of the FP32 / FP64 pipe in TFLOP/s (2 flop per FMA,

@@ -52,6 +52,33 @@ class MvrlRov6Buffers(C.Structure):
     ]
 
 
+class MvrlRov3Params(C.Structure):
+    _fields_ = [(n, _d) for n in ("rho_f", "m", "Length", "dispVol", "xg", "yg", "Izz", "Xudot", "Yvdot", "Nrdot",
+                                  "Xu", "Yv", "Yr", "Nv", "Nr", "Xuu", "Yvv", "Yrr", "Nvv", "Nrr",
+                                  "D_thruster", "thrust_coef", "alphaThruster", "l_x", "l_y", "rpm_max", "rpm_deadband")] + \
+        [("M", _d * 9), ("Minv", _d * 9), ("Ainv", _d * 12),
+         ("pid_Kp", _d * 3), ("pid_Ki", _d * 3), ("pid_Kd", _d * 3), ("pid_windup", _d * 3), ("pid_max", _d * 3)]
+
+
+MvrlRov3Config = MvrlRov6Config
+MvrlRov3Buffers = MvrlRov6Buffers  # same members, different leading dimensions per array
+
+
+class MvrlAuvParams(C.Structure):
+    _fields_ = [(n, _d) for n in ("m", "Izz", "Xuu", "Yvv", "Nrr", "Xu", "Yv", "Nr", "maxForce", "maxMoment",
+                                  "xMin", "xMax", "yMin", "yMax", "noiseMagCoeffs", "noiseMagActuation")]
+
+
+class MvrlAuvConfig(C.Structure):
+    _fields_ = [("dtype", C.c_int), ("max_steps", C.c_int), ("dt", _d), ("seed", C.c_uint64), ("env_id0", C.c_uint64),
+                ("auto_reset", C.c_int), ("stop_on_bounds", C.c_int), ("apply_noise", C.c_int), ("device", C.c_int)]
+
+
+class MvrlAuvBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "action", "obs", "reward", "done", "istep", "mults", "target", "err_o",
+                                          "recent", "ep_return", "episode", "terminal_obs", "aux", "ep_stats")]
+
+
 _vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
 
 # name -> (restype, argtypes); every symbol include/mvrl.h declares
@@ -71,6 +98,23 @@ PROTOTYPES = {
     "mvrl_angle_error": (_int, [_int, _i64, _vp, _vp, _vp, _vp]),
     "mvrl_body_axes": (_int, [_int, _i64, _i64, _vp, _vp, _vp]),
     "mvrl_measure_fma_peak": (_int, [_int, _int, _int, C.POINTER(_d), C.POINTER(_d)]),
+    "mvrl_rov6_thruster_model": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "mvrl_frame_rotate": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _int, _vp]),
+    "mvrl_rov3_default_params": (_int, [C.POINTER(MvrlRov3Params)]),
+    "mvrl_rov3_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlRov3Params), C.POINTER(MvrlRov3Config)]),
+    "mvrl_rov3_destroy": (_int, [_vp]),
+    "mvrl_rov3_derivs": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_rov3_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov3Buffers), _vp]),
+    "mvrl_rov3_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov3Buffers), _vp, C.POINTER(_d), _vp]),
+    "mvrl_rov3_thruster_model": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_auv_default_params": (_int, [C.POINTER(MvrlAuvParams)]),
+    "mvrl_auv_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlAuvParams), C.POINTER(MvrlAuvConfig)]),
+    "mvrl_auv_destroy": (_int, [_vp]),
+    "mvrl_auv_set_flow": (_int, [_vp, _vp, _int, _int, _int, _int, _d, _d, _d]),
+    "mvrl_auv_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp]),
+    "mvrl_auv_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp, _vp, _vp]),
+    "mvrl_flow_interp": (_int, [_int, _vp, _int, _int, _int, _int, _d, _d, _d, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mvrl_flow_scale": (_int, [_int, _i64, _vp, _vp, _int, _d, _d, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,306 @@
+// Legacy "verySimpleAuv" env step (K4) and turbulence-field interpolation.
+// Restates tag_00_Dec2023_simpleControlTurbulence/verySimpleAuv.py:147-410 and
+// flowGenerator.py:53-136.  One environment per thread.
+#pragma once
+#include "mvrl_math.cuh"
+#include "rov6_kernels.cuh"  // stats_accumulate
+
+namespace mvrl {
+
+// Scaled flow field on the device: [nt][ny][nx][NC] (NC = 3: u, v, Cp as in the
+// reference; NC = 2: u, v only, the copy the env kernel gathers from).
+template <typename T> struct FlowDev {
+    const T* field;
+    int nt, ny, nx, nc;
+    T dx, dy, dt;
+};
+
+// flowGenerator.py:97-136: trilinear interpolation, indices clamped to the grid,
+// weights NOT clamped (extrapolation outside, and `translate` is ignored).
+// Gathers 8 corners x NOUT components straight from L2 (read-only path).
+template <typename T, int NOUT>
+__device__ __forceinline__ void flow_interp(const FlowDev<T>& f, T time, T x, T y, T (&res)[NOUT]) {
+    const T tt = time / f.dt, xx = x / f.dx, yy = y / f.dy;
+    // clamp in floating point first: int conversion of huge / non-finite values is undefined
+    const int kk = (int)tmin(T(f.nt - 2), tmax(T(0), Real<T>::floor(tt)));
+    const int ii = (int)tmin(T(f.nx - 2), tmax(T(0), Real<T>::floor(xx)));
+    const int jj = (int)tmin(T(f.ny - 2), tmax(T(0), Real<T>::floor(yy)));
+    const T wt = tt - T(kk), wx = xx - T(ii), wy = yy - T(jj);
+    const long row = (long)f.nx * f.nc, plane = (long)f.ny * row;
+    const T* p = f.field + (long)kk * plane + (long)jj * row + (long)ii * f.nc;
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) {
+        T acc = T(0);
+#pragma unroll
+        for (int dk = 0; dk < 2; ++dk) {
+            const T* q = p + dk * plane + c;
+            const T c00 = __ldg(q), c01 = __ldg(q + f.nc), c10 = __ldg(q + row), c11 = __ldg(q + row + f.nc);
+            const T r0 = c00 * (T(1) - wx) + c01 * wx;
+            const T r1 = c10 * (T(1) - wx) + c11 * wx;
+            acc += ((T(1) - wy) * r0 + wy * r1) * (dk == 0 ? (T(1) - wt) : wt);
+        }
+        res[c] = acc;
+    }
+}
+
+template <typename T> struct AuvDev {
+    T m, Izz, Xuu, Yvv, Nrr, Xu, Yv, Nr, maxForce, maxMoment;
+    T xmin, xmax, ymin, ymax;
+    T noise_coeffs, noise_act;
+    T t_quarter;  // flow.time[nt // 4], upper bound of the random flow time offset
+};
+
+template <typename T> struct AuvStepArgs {
+    AuvDev<T> P;
+    FlowDev<T> flow;
+    long n, ld;
+    T* state;        // [6][ld] x y psi u v r
+    const T* action; // [3][ld]
+    T* obs;          // [11][ld]
+    T* reward; uint8_t* done; int32_t* istep;
+    T* mults;        // [11][ld] m I Xuu Yvv Nrr Xu Yv Nr Xact Yact Nact
+    T* target;       // [2][ld] headingTarget, flowDataTimeOffset
+    T* err_o;        // [3][ld] perr_o x, perr_o y, herr_o
+    T* recent;       // [30][ld] ring of the 10 most recent actions (slot = (iStep - 1) % 10)
+    T* ep_return;    // [ld] running episode return
+    uint32_t* episode; T* term_obs; T* aux; double* stats;
+    T dt;
+    int max_steps;
+    unsigned long long seed, env_id0;
+    int auto_reset, stop_on_bounds, apply_noise;
+};
+
+// dataToState V3, verySimpleAuv.py:147-214
+template <typename T>
+__device__ __forceinline__ void observe_auv(T x, T y, T psi, T u, T v, T r, T heading_target, T perr_ox, T perr_oy, T herr_o, T (&obs)[11]) {
+    const T px = -x, py = -y;  // positionTarget = 0
+    const T herr = angle_error(heading_target, psi);
+    obs[0] = clampt(px, T(-1), T(1));
+    obs[1] = clampt(py, T(-1), T(1));
+    obs[2] = clampt(herr / T(45. / 180. * 3.14159265358979323846), T(-1), T(1));
+    obs[3] = clampt(herr - herr_o, T(-1), T(1));
+    obs[4] = clampt(px - perr_ox, T(-1), T(1));
+    obs[5] = clampt(py - perr_oy, T(-1), T(1));
+    obs[6] = clampt(u, T(-1), T(1));
+    obs[7] = clampt(v, T(-1), T(1));
+    obs[8] = clampt(r, T(-1), T(1));
+    obs[9] = T(0);
+    obs[10] = T(0);
+}
+
+// reset draws in the reference's order (verySimpleAuv.py:222-245), Philox instead of np.random
+template <typename T>
+__device__ __forceinline__ void draw_reset_auv(const AuvDev<T>& P, unsigned long long seed, unsigned long long env, uint32_t episode,
+                                               bool apply_noise, T (&mults)[11], T* x, T* y, T* heading, T* target, T* offset) {
+    uint32_t w[16];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const uint4 q = Philox::draw(seed, env, episode, 0u, (uint32_t)b);
+        w[4 * b] = q.x; w[4 * b + 1] = q.y; w[4 * b + 2] = q.z; w[4 * b + 3] = q.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mults[k] = apply_noise ? T(1) + P.noise_coeffs / T(2) - u01<T>(w[k]) * P.noise_coeffs : T(1);
+#pragma unroll
+    for (int k = 8; k < 11; ++k) mults[k] = apply_noise ? T(1) + P.noise_act / T(2) - u01<T>(w[k]) * P.noise_act : T(1);
+    *x = (u01<T>(w[11]) - T(0.5)) * T(0.5) * (P.xmax - P.xmin);
+    *y = (u01<T>(w[12]) - T(0.5)) * T(0.5) * (P.ymax - P.ymin);
+    *heading = u01<T>(w[13]) * T(MVRL_TWO_PI);
+    *target = u01<T>(w[14]) * T(MVRL_TWO_PI);
+    *offset = u01<T>(w[15]) * P.t_quarter;
+}
+
+// K4: AuvEnv.step, verySimpleAuv.py:264-410
+template <typename T>
+__global__ void __launch_bounds__(128)
+auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const AuvDev<T>& P = a.P;
+    const long ld = a.ld;
+    T x = a.state[i], y = a.state[ld + i], psi = a.state[2 * ld + i];
+    T u = a.state[3 * ld + i], v = a.state[4 * ld + i], r = a.state[5 * ld + i];
+    const T a0 = a.action[i], a1 = a.action[ld + i], a2 = a.action[2 * ld + i];
+    T mm[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) mm[k] = a.mults[k * ld + i];
+    T heading_target = a.target[i], t_offset = a.target[ld + i];
+    const int istep = a.istep[i] + 1;
+    const T time = T(istep) * a.dt;
+    bool is_done = istep >= a.max_steps;
+
+    // recentActions.appendleft(action): ring slot, then statistics over the valid entries
+    const int slot = (istep - 1) % 10;
+    const int cnt = istep < 10 ? istep : 10;
+    T ring[10][3];
+#pragma unroll
+    for (int s = 0; s < 10; ++s) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ring[s][c] = a.recent[(s * 3 + c) * ld + i];
+    }
+#pragma unroll
+    for (int s = 0; s < 10; ++s) {
+        if (s == slot) { ring[s][0] = a0; ring[s][1] = a1; ring[s][2] = a2; }
+    }
+    a.recent[(slot * 3 + 0) * ld + i] = a0;
+    a.recent[(slot * 3 + 1) * ld + i] = a1;
+    a.recent[(slot * 3 + 2) * ld + i] = a2;
+
+    const T Fx_set = a0 * P.maxForce * mm[8], Fy_set = a1 * P.maxForce * mm[9], N_set = a2 * P.maxMoment * mm[10];
+    T sn, cs;
+    Real<T>::sincos(psi, &sn, &cs);
+    T cur[2];
+    flow_interp<T, 2>(a.flow, time + t_offset, x, y, cur);
+    const T dxv = u - cur[0], dyv = v - cur[1];
+    const T vr0 = cs * dxv + sn * dyv, vr1 = -sn * dxv + cs * dyv;
+    const T fh0 = (P.Xu * mm[5] + P.Xuu * mm[2] * tabs(vr0)) * vr0;
+    const T fh1 = (P.Yv * mm[6] + P.Yvv * mm[3] * tabs(vr1)) * vr1;
+    const T fh2 = (P.Nr * mm[7] + P.Nrr * mm[4] * tabs(r)) * r;
+    const T Fx = cs * fh0 - sn * fh1, Fy = sn * fh0 + cs * fh1;
+    const T ax = (Fx + Fx_set) / (P.m * mm[0]), ay = (Fy + Fy_set) / (P.m * mm[0]), ar = (fh2 + N_set) / (P.Izz * mm[1]);
+    // explicit Euler, position advanced with the OLD velocity (verySimpleAuv.py:321-326)
+    x = x + u * a.dt;
+    y = y + v * a.dt;
+    psi = pymod_pos(psi + r * a.dt, T(MVRL_TWO_PI));
+    u = u + ax * a.dt;
+    v = v + ay * a.dt;
+    r = r + ar * a.dt;
+
+    T obs[11];
+    observe_auv(x, y, psi, u, v, r, heading_target, a.err_o[i], a.err_o[ld + i], a.err_o[2 * ld + i], obs);
+
+    T bonus = T(0);
+    if (x < P.xmin || x > P.xmax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
+    if (y < P.ymin || y > P.ymax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
+    T perr_x = -x, perr_y = -y;
+    T herr = angle_error(heading_target, psi);
+
+    // rmsAc: mean over components of the population std of the <= 10 recent actions (:353-355)
+    T rms = T(0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T mean = T(0);
+#pragma unroll
+        for (int s = 0; s < 10; ++s) mean += (s < cnt) ? ring[s][c] : T(0);
+        mean /= T(cnt);
+        T var = T(0);
+#pragma unroll
+        for (int s = 0; s < 10; ++s) { const T d = ring[s][c] - mean; var += (s < cnt) ? d * d : T(0); }
+        rms += Real<T>::sqrt(var / T(cnt));
+    }
+    rms /= T(3);
+    const T pi = T(3.14159265358979323846);
+    const T herr_deg = tabs(herr / pi * T(180));
+    const T t0 = Real<T>::exp(T(-5) * Real<T>::sqrt(perr_x * perr_x + perr_y * perr_y));
+    const T t1 = tabs(herr) < pi / T(2) ? Real<T>::exp(T(-0.1) * herr_deg) : -Real<T>::exp(T(-0.1) * (T(180) - herr_deg));
+    const T t2 = Real<T>::exp(T(-0.6) * rms);
+    const T t3 = T(-0.1) * (a0 * a0 + a1 * a1 + a2 * a2) / T(3);
+    const T rew = t0 + t1 + t2 + t3 + bonus;
+    const T ep_ret = a.ep_return[i] + rew;
+
+    if (a.aux != nullptr) {  // the per-step log columns of verySimpleAuv.py:389-401 that are not state/obs
+        const T vals[14] = {Fx, Fy, fh2, Fx_set, Fy_set, N_set, cur[0], cur[1], rms, t0, t1, t2, t3, bonus};
+#pragma unroll
+        for (int k = 0; k < 14; ++k) a.aux[k * ld + i] = vals[k];
+    }
+    const bool bad = !(finite_t(x) && finite_t(y) && finite_t(psi) && finite_t(u) && finite_t(v) && finite_t(r));
+    if (a.stats != nullptr) stats_accumulate(a.stats, is_done && a.auto_reset, (double)istep, (double)ep_ret, bad);
+
+    int istep_out = istep;
+    T ep_ret_out = ep_ret;
+    if (is_done && a.auto_reset) {
+        if (a.term_obs != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 11; ++k) a.term_obs[k * ld + i] = obs[k];
+        }
+        const uint32_t ep = a.episode[i] + 1u;
+        a.episode[i] = ep;
+        draw_reset_auv(P, a.seed, a.env_id0 + (unsigned long long)i, ep, a.apply_noise != 0, mm, &x, &y, &psi, &heading_target, &t_offset);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) a.mults[k * ld + i] = mm[k];
+        a.target[i] = heading_target;
+        a.target[ld + i] = t_offset;
+        u = v = r = T(0);
+        istep_out = 0;
+        ep_ret_out = T(0);
+        perr_x = -x; perr_y = -y;
+        herr = angle_error(heading_target, psi);
+        observe_auv(x, y, psi, u, v, r, heading_target, perr_x, perr_y, herr, obs);
+    }
+    a.state[i] = x; a.state[ld + i] = y; a.state[2 * ld + i] = psi;
+    a.state[3 * ld + i] = u; a.state[4 * ld + i] = v; a.state[5 * ld + i] = r;
+    a.err_o[i] = perr_x; a.err_o[ld + i] = perr_y; a.err_o[2 * ld + i] = herr;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a.obs[k * ld + i] = obs[k];
+    a.reward[i] = rew;
+    a.done[i] = is_done ? 1 : 0;
+    a.istep[i] = istep_out;
+    a.ep_return[i] = ep_ret_out;
+}
+
+template <typename T> struct AuvResetArgs {
+    AuvDev<T> P;
+    long n, ld;
+    T* state; T* obs; int32_t* istep; T* mults; T* target; T* err_o; T* recent; T* ep_return;
+    const uint32_t* episode; const uint8_t* mask;
+    const T* init;  // nullable [4][ld]: x, y, heading, headingTarget (fixedInitialValues)
+    unsigned long long seed, env_id0;
+    int apply_noise;
+};
+
+// AuvEnv.reset, verySimpleAuv.py:216-262
+template <typename T>
+__global__ void __launch_bounds__(128)
+auv_reset_kernel(const __grid_constant__ AuvResetArgs<T> a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (a.mask != nullptr && a.mask[i] == 0) return;
+    const long ld = a.ld;
+    T mm[11], x, y, psi, target, offset;
+    draw_reset_auv(a.P, a.seed, a.env_id0 + (unsigned long long)i, a.episode ? a.episode[i] : 0u, a.apply_noise != 0, mm, &x, &y, &psi, &target, &offset);
+    if (a.init != nullptr) { x = a.init[i]; y = a.init[ld + i]; psi = a.init[2 * ld + i]; target = a.init[3 * ld + i]; }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a.mults[k * ld + i] = mm[k];
+    a.state[i] = x; a.state[ld + i] = y; a.state[2 * ld + i] = psi;
+    a.state[3 * ld + i] = T(0); a.state[4 * ld + i] = T(0); a.state[5 * ld + i] = T(0);
+    a.target[i] = target; a.target[ld + i] = offset;
+    a.istep[i] = 0;
+    a.ep_return[i] = T(0);
+#pragma unroll
+    for (int k = 0; k < 30; ++k) a.recent[k * ld + i] = T(0);
+    const T herr = angle_error(target, psi);
+    a.err_o[i] = -x; a.err_o[ld + i] = -y; a.err_o[2 * ld + i] = herr;
+    T obs[11];
+    observe_auv(x, y, psi, T(0), T(0), T(0), target, -x, -y, herr, obs);
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a.obs[k * ld + i] = obs[k];
+}
+
+// stand-alone ReconstructedFlow.interp: t [n], xy [2][ld] -> out [3][ld]
+template <typename T>
+__global__ void flow_interp_kernel(const FlowDev<T> f, long n, long ld, const T* t, const T* xy, T* out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (f.nc == 3) {
+        T r[3];
+        flow_interp<T, 3>(f, t[i], xy[i], xy[ld + i], r);
+        out[i] = r[0]; out[ld + i] = r[1]; out[2 * ld + i] = r[2];
+    } else {
+        T r[2];
+        flow_interp<T, 2>(f, t[i], xy[i], xy[ld + i], r);
+        out[i] = r[0]; out[ld + i] = r[1];
+    }
+}
+
+// ReconstructedFlow.scale (flowGenerator.py:80-90) on the field values: base [cells][3] -> out [cells][nc_out]
+template <typename T>
+__global__ void flow_scale_kernel(long cells, const T* base, T* out, int nc_out, T vel, T turb) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const T u = (base[3 * i] * vel - vel) * turb + vel;
+    const T v = (base[3 * i + 1] * vel - T(0)) * turb;
+    out[nc_out * i] = u;
+    out[nc_out * i + 1] = v;
+    if (nc_out == 3) out[3 * i + 2] = base[3 * i + 2] / tmax(T(1e-6), (vel * turb) * (vel * turb));
+}
+
+}  // namespace mvrl

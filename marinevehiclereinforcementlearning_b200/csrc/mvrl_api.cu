@@ -9,7 +9,7 @@
 #include <cstring>
 #include <new>
 
-#include "../../include/mvrl.h"
+#include "mvrl_host.h"
 #include "rov6_kernels.cuh"
 
 using namespace mvrl;
@@ -27,13 +27,6 @@ int mvrl_fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define MVRL_CUDA(call)                                                                     \
-    do {                                                                                    \
-        cudaError_t e_ = (call);                                                            \
-        if (e_ != cudaSuccess)                                                              \
-            return mvrl_fail(MVRL_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
 extern "C" MVRL_API int mvrl_version(void) { return MVRL_VERSION; }
 extern "C" MVRL_API const char* mvrl_last_error(void) { return g_err; }
 extern "C" MVRL_API int mvrl_device_count(void) {
@@ -45,7 +38,7 @@ extern "C" MVRL_API int mvrl_device_count(void) {
 // ---------------------------------------------------------------------------
 // small dense linear algebra for mvrl_rov6_default_params (host, long double)
 // ---------------------------------------------------------------------------
-static bool invert_n(const double* a, double* out, int n) {
+bool mvrl_invert_n(const double* a, double* out, int n) {
     long double w[6][12];
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) { w[i][j] = a[i * n + j]; w[i][n + j] = (i == j) ? 1.0L : 0.0L; }
@@ -93,7 +86,7 @@ extern "C" MVRL_API int mvrl_rov6_default_params(MvrlRov6Params* p) {
     const double Ma[6] = {-p->Xudot, -p->Yvdot, -Zvdot, -p->Kpdot, -p->Mqdot, -p->Nrdot};
     for (int i = 0; i < 36; ++i) p->M[i] = Mrb[i];
     for (int i = 0; i < 6; ++i) p->M[i * 6 + i] += Ma[i];
-    if (!invert_n(p->M, p->Minv, 6)) return mvrl_fail(MVRL_EINVAL, "singular mass matrix");
+    if (!mvrl_invert_n(p->M, p->Minv, 6)) return mvrl_fail(MVRL_EINVAL, "singular mass matrix");
     // thruster geometry, 6DoF.py:164-212, and allocation, resources.py:19-35
     const double al = 33. / 180. * pi, lx = 0.1475, ly = 0.101, lz = 0.068, lxv = 0.120, lyv = 0.22, lzv = 0.0;
     const double pos[8][3] = {{lx, ly, lz}, {lx, -ly, lz}, {-lx, ly, lz}, {-lx, -ly, lz},
@@ -113,7 +106,7 @@ extern "C" MVRL_API int mvrl_rov6_default_params(MvrlRov6Params* p) {
         long double s = 0; for (int k = 0; k < 8; ++k) s += (long double)p->A[i * 8 + k] * p->A[j * 8 + k];
         AAt[i * 6 + j] = (double)s;
     }
-    if (!invert_n(AAt, AAtInv, 6)) return mvrl_fail(MVRL_EINVAL, "rank-deficient allocation matrix");
+    if (!mvrl_invert_n(AAt, AAtInv, 6)) return mvrl_fail(MVRL_EINVAL, "rank-deficient allocation matrix");
     for (int i = 0; i < 8; ++i) for (int j = 0; j < 6; ++j) {
         long double s = 0; for (int k = 0; k < 6; ++k) s += (long double)p->A[k * 8 + i] * AAtInv[k * 6 + j];
         p->Ainv[i * 6 + j] = (double)s;
@@ -201,12 +194,7 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     if (cfg->n_sub < 1) return mvrl_fail(MVRL_EINVAL, "n_sub must be >= 1");
     if (!(cfg->dt > 0)) return mvrl_fail(MVRL_EINVAL, "dt must be > 0");
     if (!(params->thrust_coef > 0)) return mvrl_fail(MVRL_EINVAL, "thrust_coef must be > 0");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return mvrl_fail(MVRL_ENODEV, "no CUDA device: libmvrl has no CPU path");
-    }
-    if (cfg->device < 0 || cfg->device >= ndev) return mvrl_fail(MVRL_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    { const int rc = mvrl_require_device(cfg->device); if (rc != MVRL_OK) return rc; }
     MvrlRov6* h = new (std::nothrow) MvrlRov6();
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
     h->p = *params;
@@ -221,11 +209,16 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
 extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) { delete h; return MVRL_OK; }
 extern "C" MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h) { return (h && h->sp) ? 1 : 0; }
 
-static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+#define grid_for mvrl_grid_for
+#define check_launch mvrl_check_launch
 
-static int check_launch(const char* what) {
-    cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) { cudaGetLastError(); return mvrl_fail(MVRL_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e)); }
+int mvrl_require_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return mvrl_fail(MVRL_ENODEV, "no CUDA device: libmvrl has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return mvrl_fail(MVRL_EINVAL, "device %d out of range (%d devices)", device, ndev);
     return MVRL_OK;
 }
 
@@ -506,4 +499,55 @@ extern "C" MVRL_API int mvrl_measure_fma_peak(int dtype, int device, int iters, 
     *tflops_out = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     return check_launch("fma_peak");
+}
+
+// ---------------------------------------------------------------------------
+// small pieces of the BlueROV2Heavy6DoF surface used by the single-vehicle API
+// ---------------------------------------------------------------------------
+// thrusterModel(rpm), 6DoF.py:233-236 (no saturation / deadband: those are applied by forceModel)
+template <typename T>
+__global__ void rov6_thruster_kernel(T thrust_k, long n, const T* rpm, T* F) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) F[i] = thrust_k * rpm[i] * tabs(rpm[i]);
+}
+
+extern "C" MVRL_API int mvrl_rov6_thruster_model(MvrlRov6* h, int64_t n, const void* rpm, void* F, mvrl_stream_t stream) {
+    if (!h || !rpm || !F || n < 0) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_thruster_model: bad argument");
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->c.dtype == MVRL_F64) rov6_thruster_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(h->pd.thrust_k, n, (const double*)rpm, (double*)F);
+    else rov6_thruster_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(h->pf.thrust_k, n, (const float*)rpm, (float*)F);
+    return check_launch("rov6_thruster_model");
+}
+
+// globalToVehicle (to_vehicle = 1, 6DoF.py:244-248) / vehicleToGlobal (0, 6DoF.py:250-251)
+template <typename T>
+__global__ void frame_rotate_kernel(long n, long ld, const T* axes, const T* v, T* out, int to_vehicle) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T ax[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ax[k] = axes[k * ld + i];
+    const T a = v[i], b = v[ld + i], c = v[2 * ld + i];
+    if (to_vehicle) {
+        out[i] = a * ax[0] + b * ax[1] + c * ax[2];
+        out[ld + i] = a * ax[3] + b * ax[4] + c * ax[5];
+        out[2 * ld + i] = a * ax[6] + b * ax[7] + c * ax[8];
+    } else {
+        out[i] = a * ax[0] + b * ax[3] + c * ax[6];
+        out[ld + i] = a * ax[1] + b * ax[4] + c * ax[7];
+        out[2 * ld + i] = a * ax[2] + b * ax[5] + c * ax[8];
+    }
+}
+
+extern "C" MVRL_API int mvrl_frame_rotate(int dtype, int64_t n, int64_t ld, const void* axes, const void* v, void* out, int to_vehicle,
+                                          mvrl_stream_t stream) {
+    if (!axes || !v || !out || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_frame_rotate: bad argument");
+    if (n == 0) return MVRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) frame_rotate_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)axes, (const double*)v, (double*)out, to_vehicle);
+    else if (dtype == MVRL_F32) frame_rotate_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)axes, (const float*)v, (float*)out, to_vehicle);
+    else return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    return check_launch("frame_rotate");
 }

@@ -127,8 +127,9 @@ class Rov6Constants:
         return (id(self), self._version)
 
 
-class Rov6Handle:
-    """RAII wrapper of an ``MvrlRov6*``."""
+class _Handle:
+    """RAII wrapper of an opaque libmvrl handle (MvrlRov6* / MvrlRov3*)."""
+    PREFIX = "mvrl_rov6"
 
     def __init__(self, consts, dtype, action_mode, n_sub=8, dt=0.2, max_steps=250, seed=0, env_id0=0,
                  auto_reset=False, fixed_sp=False, device=0, fast_math=False):
@@ -141,20 +142,27 @@ class Rov6Handle:
         self.cfg = cfg
         self.params = consts.to_struct()
         self._h = C.c_void_p()
-        _lib.check(self.lib.mvrl_rov6_create(C.byref(self._h), C.byref(self.params), C.byref(cfg)))
+        _lib.check(getattr(self.lib, self.PREFIX + "_create")(C.byref(self._h), C.byref(self.params), C.byref(cfg)))
 
-    @property
-    def specialised(self):
-        return bool(self.lib.mvrl_rov6_is_specialised(self._h))
+    def fn(self, name):
+        return getattr(self.lib, "%s_%s" % (self.PREFIX, name))
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             try:
-                self.lib.mvrl_rov6_destroy(h)
+                getattr(self.lib, self.PREFIX + "_destroy")(h)
             except Exception:
                 pass
             self._h = None
+
+
+class Rov6Handle(_Handle):
+    PREFIX = "mvrl_rov6"
+
+    @property
+    def specialised(self):
+        return bool(self.lib.mvrl_rov6_is_specialised(self._h))
 
 
 def _device_index(device):
@@ -165,18 +173,22 @@ def _device_index(device):
     return d.index if d.index is not None else torch.cuda.current_device()
 
 
-class BlueROV2Heavy6DoFVecEnv:
-    """N BlueROV2 Heavy 6DoF environments stepped by one fused CUDA kernel.
+class _RovVecEnv:
+    """N vehicle environments stepped by one fused CUDA kernel (shared host logic
+    of the 6DoF and 3DoF batched envs).
 
-    Semantics per environment are those of the reference's
-    ``BlueROV2Heavy6DoFEnv`` (6DoF.py:445-594) with the integrator fixed to
-    classic RK4 x ``n_sub``; the batch follows the SB3 ``VecEnv`` convention
-    (``step`` -> obs, rewards, dones, infos; auto-reset with
-    ``terminal_observation``).  Tensors stay on the device.  Internally every
-    array is structure-of-arrays ``[field, ld]``; ``obs``/``actions`` are
-    exposed as ``[N, k]`` views of them (``*_fm`` gives the feature-major
+    Semantics per environment are those of the reference's Gym env with the
+    integrator fixed to classic RK4 x ``n_sub``; the batch follows the SB3
+    ``VecEnv`` convention (``step`` -> obs, rewards, dones, infos; auto-reset
+    with ``terminal_observation``).  Tensors stay on the device.  Internally
+    every array is structure-of-arrays ``[field, ld]``; ``obs`` / ``actions``
+    are exposed as ``[N, k]`` views of them (``*_fm`` gives the feature-major
     tensors for transposition-free policies).
     """
+    HANDLE = Rov6Handle
+    CONSTANTS = None
+    STATE_DIM, OBS_DIM, SP_DIM, PATH_DIM, CTRL_DIM, AUX_DIM = 12, 9, 6, 6, 13, 14
+    ACTION_DIM = {ACT_RPM: 8, ACT_FORCE: 6, ACT_SETPOINT: 6}
 
     def __init__(self, num_envs, seed=0, dt=0.2, maxSteps=250, n_sub=8, action_mode="setpoint",
                  dtype=torch.float32, device="cuda", auto_reset=True, env_id0=0, fast_math=False,
@@ -184,26 +196,28 @@ class BlueROV2Heavy6DoFVecEnv:
         self.num_envs = int(num_envs)
         self.dt, self._max_episode_steps, self.n_sub = float(dt), int(maxSteps), int(n_sub)
         self.action_mode = ACTION_MODES[action_mode]
+        if self.action_mode not in self.ACTION_DIM:
+            raise ValueError("action_mode %r is not supported by %s" % (action_mode, type(self).__name__))
         self.dtype, self.seed, self.env_id0 = dtype, int(seed), int(env_id0)
         self.auto_reset, self.fast_math = bool(auto_reset), bool(fast_math)
         self.device = torch.device("cuda", _device_index(device))
-        self.vehicle = vehicle if vehicle is not None else Rov6Constants()
-        self.lenAction = ACTION_DIM[self.action_mode]
-        self.lenObs = 9
+        self.vehicle = vehicle if vehicle is not None else self.CONSTANTS()
+        self.lenAction = self.ACTION_DIM[self.action_mode]
+        self.lenObs = self.OBS_DIM
         self.fixedSp = False
         n = self.num_envs
         self.ld = ((n + 31) // 32) * 32
         ld, dev = self.ld, self.device
         z = lambda k: torch.zeros((k, ld), dtype=dtype, device=dev)
-        self._state, self._action, self._obs = z(12), z(self.lenAction), z(9)
+        self._state, self._action, self._obs = z(self.STATE_DIM), z(self.lenAction), z(self.OBS_DIM)
         self._reward = torch.zeros(ld, dtype=dtype, device=dev)
         self._done = torch.zeros(ld, dtype=torch.uint8, device=dev)
         self._istep = torch.zeros(ld, dtype=torch.int32, device=dev)
-        self._setpoint, self._path = z(6), z(6)
-        self._ctrl = z(13)
+        self._setpoint, self._path = z(self.SP_DIM), z(self.PATH_DIM)
+        self._ctrl = z(self.CTRL_DIM)
         self._episode = torch.zeros(ld, dtype=torch.int32, device=dev)  # reinterpreted as uint32
-        self._terminal_obs = z(9) if (record_terminal_obs and auto_reset) else None
-        self._aux = z(14) if record_aux else None
+        self._terminal_obs = z(self.OBS_DIM) if (record_terminal_obs and auto_reset) else None
+        self._aux = z(self.AUX_DIM) if record_aux else None
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev) if collect_stats else None
         if self._stats is not None:
             self._reset_stats()
@@ -224,10 +238,10 @@ class BlueROV2Heavy6DoFVecEnv:
         key = (self.vehicle.fingerprint(), self.fixedSp, self.auto_reset, self.n_sub, self.dt,
                self._max_episode_steps, self.seed, self.env_id0, self.fast_math, self.action_mode)
         if self._handle is None or key != self._handle_key:
-            self._handle = Rov6Handle(self.vehicle, self.dtype, self.action_mode, n_sub=self.n_sub, dt=self.dt,
-                                      max_steps=self._max_episode_steps, seed=self.seed, env_id0=self.env_id0,
-                                      auto_reset=self.auto_reset, fixed_sp=self.fixedSp, device=self.device.index,
-                                      fast_math=self.fast_math)
+            self._handle = self.HANDLE(self.vehicle, self.dtype, self.action_mode, n_sub=self.n_sub, dt=self.dt,
+                                       max_steps=self._max_episode_steps, seed=self.seed, env_id0=self.env_id0,
+                                       auto_reset=self.auto_reset, fixed_sp=self.fixedSp, device=self.device.index,
+                                       fast_math=self.fast_math)
             self._handle_key = key
         return self._handle
 
@@ -259,8 +273,8 @@ class BlueROV2Heavy6DoFVecEnv:
 
     @property
     def path(self):
-        """[N, 2, 3] way-points (6DoF.py:497, 509)."""
-        return self._path[:, :self.num_envs].T.reshape(self.num_envs, 2, 3)
+        """[N, 2, dims] way-points (6DoF.py:497, 509 / 3DoF.py:423, 435)."""
+        return self._path[:, :self.num_envs].T.reshape(self.num_envs, 2, self.PATH_DIM // 2)
 
     @property
     def iStep(self):
@@ -272,8 +286,9 @@ class BlueROV2Heavy6DoFVecEnv:
 
     # -- reset / step ------------------------------------------------------------
     def reset(self, initialSetpoint=None, mask=None):
-        """6DoF.py:485-529.  ``initialSetpoint=None`` takes the random branch
-        (defined here; the reference's own line raises - see DESIGN.md)."""
+        """6DoF.py:485-529 / 3DoF.py:411-453.  ``initialSetpoint=None`` takes the
+        random branch (for 6DoF defined here; the reference's own line raises -
+        see DESIGN.md)."""
         self.fixedSp = initialSetpoint is not None
         h = self._get_handle()
         if self._needs_episode_bump:
@@ -284,12 +299,13 @@ class BlueROV2Heavy6DoFVecEnv:
         self._needs_episode_bump = True
         sp = None
         if initialSetpoint is not None:
-            sp = (C.c_double * 6)(*[float(v) for v in np.asarray(initialSetpoint, dtype=float).reshape(6)])
+            vals = [float(v) for v in np.asarray(initialSetpoint, dtype=float).reshape(self.SP_DIM)]
+            sp = (C.c_double * self.SP_DIM)(*vals)
         m = None
         if mask is not None:
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        _lib.check(h.lib.mvrl_rov6_reset(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.ptr(m), sp,
-                                         _lib.current_stream(self.device)))
+        _lib.check(h.fn("reset")(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.ptr(m), sp,
+                                 _lib.current_stream(self.device)))
         return self.state
 
     def set_actions(self, actions):
@@ -310,7 +326,7 @@ class BlueROV2Heavy6DoFVecEnv:
         if actions is not None:
             self.set_actions(actions)
         h = self._get_handle()
-        _lib.check(h.lib.mvrl_rov6_step(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.current_stream(self.device)))
+        _lib.check(h.fn("step")(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.current_stream(self.device)))
 
     def step(self, actions=None):
         self.step_async(actions)
@@ -320,37 +336,39 @@ class BlueROV2Heavy6DoFVecEnv:
             infos["terminal_observation"] = self._terminal_obs[:, :n].T
         return self.state, self._reward[:n], self._done[:n].bool(), infos
 
+    def observe(self):
+        """dataToState for the current device state (6DoF.py:467-483 / 3DoF.py:397-409),
+        [N, obs]: resources.angleError / clip run on the device through torch views of the
+        same SoA buffers the kernels use."""
+        from . import resources
+        n, L3 = self.num_envs, self.vehicle.Length * 3.
+        half = self.PATH_DIM // 2
+        pos = self._state[:half, :n]
+        ang_sp = self._setpoint[half:, :n]
+        ang = self._state[half:self.SP_DIM, :n]
+        err = torch.stack([resources.angleError(ang_sp[k].contiguous(), ang[k].contiguous()) for k in range(ang.shape[0])])
+        obs = torch.cat([(self._path[:half, :n] - pos) / L3, (self._path[half:, :n] - pos) / L3, err / (45. / 180. * np.pi)])
+        return obs.clamp(-1., 1.).T
+
     # -- episode statistics (K5): device-side accumulators + optional all-reduce
     def episode_stats(self, reduce_group=None, reset=True):
         """{episodes, mean_length, mean_return, min_return, max_return,
-        nonfinite}.  With ``reduce_group`` the 8 accumulators are all-reduced
-        over the process group (NCCL on GPUs) - the only collective of the
-        framework, off the step path."""
+        nonfinite}.  When torch.distributed is initialised the 8 accumulators
+        are all-reduced over the process group (NCCL on GPUs) - the only
+        collective of the framework, off the step path."""
         if self._stats is None:
             raise RuntimeError("collect_stats=False")
-        s = self._stats.clone()
-        if reduce_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            import torch.distributed as dist
-            sums = s[[0, 1, 2, 5]].clone()
-            mn, mx = s[3:4].clone(), s[4:5].clone()
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=reduce_group)
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=reduce_group)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=reduce_group)
-            s[[0, 1, 2, 5]] = sums
-            s[3], s[4] = mn[0], mx[0]
+        from .distributed import reduce_episode_stats
+        out = reduce_episode_stats(self._stats, group=reduce_group)
         if reset:
             self._reset_stats()
-        v = s.tolist()
-        n_ep = v[0]
-        return {"episodes": int(n_ep), "mean_length": v[1] / n_ep if n_ep else math.nan,
-                "mean_return": v[2] / n_ep if n_ep else math.nan,
-                "min_return": v[3] if n_ep else math.nan, "max_return": v[4] if n_ep else math.nan,
-                "nonfinite": int(v[5])}
+        return out
 
     # -- checkpoint / resume -------------------------------------------------------
+    _STATE_KEYS = ("_state", "_istep", "_setpoint", "_path", "_ctrl", "_episode", "_obs")
+
     def state_dict(self):
-        keys = ("_state", "_istep", "_setpoint", "_path", "_ctrl", "_episode", "_obs")
-        d = {k: getattr(self, k).clone() for k in keys}
+        d = {k: getattr(self, k).clone() for k in self._STATE_KEYS}
         d["fixedSp"] = self.fixedSp
         return d
 
@@ -361,6 +379,15 @@ class BlueROV2Heavy6DoFVecEnv:
             else:
                 getattr(self, k).copy_(v)
         self._needs_episode_bump = True
+
+
+class BlueROV2Heavy6DoFVecEnv(_RovVecEnv):
+    """Batched ``BlueROV2Heavy6DoFEnv`` (6DoF.py:445-594): 12 states, 9
+    observations; actions per ``action_mode``: "setpoint" (reference Gym
+    semantics, 6 in [-1, 1]), "force" (6 earth-frame generalised forces) or
+    "rpm" (8 thruster rpm)."""
+    HANDLE = Rov6Handle
+    CONSTANTS = Rov6Constants
 
 
 class Rov6Derivs:
