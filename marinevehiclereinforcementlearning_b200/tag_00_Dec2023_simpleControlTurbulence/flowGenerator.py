@@ -1,0 +1,92 @@
+"""Drop-in for tag_00_Dec2023_simpleControlTurbulence/flowGenerator.py:
+``ReconstructedFlow`` with ``scale`` / ``interp`` / ``interpField`` running as
+CUDA kernels on a device-resident field (see ``auv.FlowField``)."""
+import os
+
+import numpy as np
+import torch
+
+from ..auv import FlowField
+
+
+def synthetic_base_field(lt_mean, nt, seed=7, sigma=0.05):
+    """Stand-in for the SPOD reconstruction when ``coeffs.npy`` / ``modes_r.npy`` are
+    unavailable (they are absent from the reference checkout): long-time mean +
+    seeded Gaussian fluctuations, ``[nt, Ny, Nx, 3]``."""
+    rng = np.random.default_rng(seed)
+    lt_mean = np.asarray(lt_mean, dtype=float)
+    return lt_mean[None] + sigma * rng.standard_normal((nt,) + lt_mean.shape)
+
+
+class ReconstructedFlow(FlowField):
+    """flowGenerator.py:13-159.  ``ReconstructedFlow(dataDir)`` reads the same
+    files as the reference (``coeffs.npy``, ``modes_r.npy``, ``ltm.npy``,
+    ``params_coeffs.yaml``, ``turbulence_coords.npy``) and raises
+    ``FileNotFoundError`` like the reference when one is missing;
+    ``ReconstructedFlow.from_base_field`` / ``.synthetic`` build the object from
+    an explicit base field instead."""
+
+    def __init__(self, dataDir, dtype=torch.float32, device="cuda"):
+        import yaml
+        coeffs = np.load(os.path.join(dataDir, "coeffs.npy"))
+        modes = np.load(os.path.join(dataDir, "modes_r.npy"))
+        self.lt_mean = np.load(os.path.join(dataDir, "ltm.npy"))
+        # flowGenerator.py:20-23: baseFlowData[t] = Re(modes @ coeffs[:, t]) + mean - one GEMM
+        # [Ny*Nx*3, nModes] x [nModes, Nt] on the device instead of a Python loop over time levels
+        dev = torch.device(device)
+        m = torch.as_tensor(modes, device=dev)
+        c = torch.as_tensor(coeffs, device=dev).to(m.dtype)
+        rec = torch.matmul(m.reshape(-1, m.shape[-1]), c)
+        rec = (rec.real if rec.is_complex() else rec).T.reshape((c.shape[1],) + tuple(m.shape[:-1]))
+        base = rec.to(torch.float64) + torch.as_tensor(self.lt_mean, device=dev)
+        with open(os.path.join(dataDir, "params_coeffs.yaml"), "r") as infile:
+            params = yaml.safe_load(infile)
+        coords = np.load(os.path.join(dataDir, "turbulence_coords.npy"))
+        dx, dy = self._check_spacing(coords)
+        super().__init__(base, baseDx=dx, baseDy=dy, baseDt=params["time_step"], baseCoords=coords, dtype=dtype, device=device)
+
+    @staticmethod
+    def _check_spacing(coords):
+        """flowGenerator.py:32-42: the grid must be uniform in x and in y ((y, x) orientation)."""
+        dx = coords[0, 1:, 0] - coords[0, :-1, 0]
+        dy = coords[1:, 0, 1] - coords[:-1, 0, 1]
+        if not np.all(np.abs(dx - dx[0]) < 1e-6):
+            raise ValueError("Non-uniform input grid spacing in the x-direction")
+        if not np.all(np.abs(dy - dy[0]) < 1e-6):
+            raise ValueError("Non-uniform input grid spacing in the y-direction")
+        return float(dx[0]), float(dy[0])
+
+    @classmethod
+    def from_base_field(cls, baseFlowData, baseDx=0.005, baseDy=0.005, baseDt=0.002, baseCoords=None, lt_mean=None,
+                        dtype=torch.float32, device="cuda"):
+        self = cls.__new__(cls)
+        self.lt_mean = lt_mean
+        FlowField.__init__(self, baseFlowData, baseDx=baseDx, baseDy=baseDy, baseDt=baseDt, baseCoords=baseCoords, dtype=dtype, device=device)
+        return self
+
+    @classmethod
+    def synthetic(cls, dataDir=None, lt_mean=None, nt=2000, seed=7, sigma=0.05, dtype=torch.float32, device="cuda"):
+        """Mean field (``ltm.npy`` of ``dataDir`` or ``lt_mean``) + seeded noise, ``nt`` time levels."""
+        coords, dx, dy, dt = None, 0.005, 0.005, 0.002
+        if lt_mean is None:
+            lt_mean = np.load(os.path.join(dataDir, "ltm.npy"))
+            cpath = os.path.join(dataDir, "turbulence_coords.npy")
+            if os.path.exists(cpath):
+                coords = np.load(cpath)
+                dx, dy = cls._check_spacing(coords)
+        return cls.from_base_field(synthetic_base_field(lt_mean, nt, seed, sigma), baseDx=dx, baseDy=dy, baseDt=dt,
+                                   baseCoords=coords, lt_mean=np.asarray(lt_mean), dtype=dtype, device=device)
+
+    # turbulence intensity on the plane, flowGenerator.py:47-51 (computed lazily: the env never needs it)
+    def _intensity(self):
+        f = self.baseFlowData  # == flowData after scale(1, 1, 1), where the reference evaluates it
+        self.uPrime = torch.sqrt(torch.sum((f[..., 0] - 1.) ** 2., dim=0) / f.shape[0]).cpu().numpy()
+        self.vPrime = torch.sqrt(torch.sum((f[..., 1] - 0.) ** 2., dim=0) / f.shape[0]).cpu().numpy()
+        self.TI = np.sqrt(0.5 * (self.uPrime + self.vPrime))
+        self.baseTI = self.TI[self.TI.shape[0] // 2, self.TI.shape[1] // 2]
+
+    def __getattr__(self, name):
+        if name in ("uPrime", "vPrime", "TI", "baseTI"):
+            self._intensity()
+            return self.__dict__[name]
+        raise AttributeError(name)

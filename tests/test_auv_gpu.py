@@ -1,0 +1,167 @@
+"""GPU parity tests of the legacy path (kernel K4: AuvEnv step with the
+turbulence-field gather, ReconstructedFlow.scale / interp) through the C ABI:
+vs the golden episodes produced by the unmodified reference and vs the numpy
+oracle.  fp64 within 1e-8, fp32 within 1e-4 (north_star trajectory bars)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from marinevehiclereinforcementlearning_b200.auv import AuvVecEnv
+    from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence import flowGenerator, verySimpleAuv
+    from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence.resources import headingError
+
+DEV = "cuda"
+
+
+def rel_err(a, ref):
+    ref = np.asarray(ref)
+    scale = np.abs(ref) + np.abs(ref).max(axis=-1, keepdims=True)
+    return (np.abs(np.asarray(a) - ref) / np.maximum(scale, 1e-300)).max()
+
+
+def base_field(g, nt=None):
+    nt = int(g["nt"]) if nt is None else nt
+    return g["ltm"][None] + 0.05 * np.random.default_rng(7).standard_normal((nt,) + g["ltm"].shape)
+
+
+def make_flows(g, dtype=torch.float64, nt=None):
+    base = base_field(g, nt)
+    flow = flowGenerator.ReconstructedFlow.from_base_field(base, float(g["base_dx"]), float(g["base_dy"]), float(g["base_dt"]),
+                                                           dtype=dtype, device=DEV)
+    ref = o.FlowOracle(base, float(g["base_dx"]), float(g["base_dy"]), float(g["base_dt"]))
+    flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    ref.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    return flow, ref
+
+
+def test_flow_scale_interp_vs_reference_golden():
+    g = load_golden("legacy")
+    flow, _ = make_flows(g)
+    assert flow.dx == float(g["scaled_dx"]) and flow.dy == float(g["scaled_dy"]) and flow.dt == float(g["scaled_dt"])
+    assert np.abs(flow.flowData[::7, ::5, ::6, :].cpu().numpy() - g["scaled_field_sample"]).max() < 1e-14
+    res = flow.interp(torch.as_tensor(g["interp_t"], device=DEV), torch.as_tensor(g["interp_xy"], device=DEV)).cpu().numpy()
+    assert rel_err(res, g["interp_res"]) < 1e-11
+    # scalar call signature of the reference: interp(time, (x, y)) -> (3,)
+    one = flow.interp(float(g["interp_t"][5]), (float(g["interp_xy"][5, 0]), float(g["interp_xy"][5, 1])))
+    assert one.shape == (3,) and rel_err(one, g["interp_res"][5]) < 1e-11
+    for k, t in enumerate(g["interp_field_t"]):
+        assert rel_err(flow.interpField(float(t)).cpu().numpy(), g["interp_field"][k]) < 1e-11
+    assert flow.time[flow.time.shape[0] // 4] == float(g["flow_time_quarter"])
+    got = headingError(g["heading_pairs"][:, 0], g["heading_pairs"][:, 1])
+    assert np.abs(got - g["heading_err"]).max() < 1e-14
+
+
+def test_flow_interp_fp32_and_out_of_range():
+    g = load_golden("legacy")
+    flow, ref = make_flows(g, torch.float32)
+    rng = np.random.default_rng(5)
+    n = 50_000
+    t = rng.uniform(-0.1, ref.time[-1] * 1.2, n)
+    xy = np.stack([rng.uniform(-1.5, 4.0, n), rng.uniform(-1.5, 3.0, n)], axis=1)
+    got = flow.interp(torch.as_tensor(t, device=DEV), torch.as_tensor(xy, device=DEV)).cpu().numpy()
+    want = ref.interp(t, xy)
+    assert np.abs(got[:, :2] - want[:, :2]).max() / np.abs(want[:, :2]).max() < 2e-5
+
+
+def install(env, g, e):
+    """Start episode e of the golden file: the values the reference's RNG drew."""
+    env.reset(applyNoise=False, fixedInitialValues=[g["ep_pos0"][e], float(g["ep_heading0"][e]), float(g["ep_heading_target"][e])])
+    env._mults[:, 0] = torch.as_tensor(g["ep_mults"][e], dtype=env.dtype, device=DEV)
+    env._target[1, 0] = float(g["ep_t_offset"][e])
+
+
+def test_episodes_fp64_vs_reference_golden():
+    g = load_golden("legacy")
+    flow, _ = make_flows(g)
+    for e in range(g["ep_actions"].shape[0]):
+        env = AuvVecEnv(1, flow, dtype=torch.float64, noiseMagCoeffs=0.1, noiseMagActuation=0.1, stopOnBoundsExceeded=(e != 1),
+                        maxSteps=50 if e == 2 else 250, auto_reset=False, record_aux=True)
+        install(env, g, e)
+        assert np.abs(env.state.cpu().numpy()[0] - g["ep_obs0"][e]).max() < 1e-14
+        n_done = 0
+        for k in range(g["ep_actions"].shape[1]):
+            ob, r, d, _ = env.step(torch.as_tensor(g["ep_actions"][e, k:k + 1], device=DEV))
+            assert np.abs(ob.cpu().numpy()[0] - g["ep_obs"][e, k]).max() < 1e-9, (e, k)
+            assert abs(float(r[0]) - g["ep_reward"][e, k]) < 1e-8 * max(1.0, abs(g["ep_reward"][e, k])), (e, k)
+            assert bool(d[0]) == bool(g["ep_done"][e, k]), (e, k)
+            h = g["ep_history"][e, k]
+            aux = env._aux[:, 0].cpu().numpy()
+            assert rel_err(aux[0:6], h[9:15]) < 1e-10 and np.abs(aux[6:9] - h[18:21]).max() < 1e-10
+            assert np.abs(aux[9:14] - h[21:26]).max() < 1e-9
+            s = env._state[:, 0].cpu().numpy()
+            assert rel_err(s[[0, 1, 2]], h[3:6]) < 1e-10 and rel_err(s[3:6], h[15:18]) < 1e-10
+            if d[0]:
+                n_done += 1
+                break
+        assert n_done == int(g["ep_done"][e].any())
+
+
+def test_single_env_dropin_vs_reference_golden():
+    """AuvEnv with the reference's constructor / reset / step signatures and its 40-column timeHistory."""
+    g = load_golden("legacy")
+    flow = flowGenerator.ReconstructedFlow.from_base_field(base_field(g), float(g["base_dx"]), float(g["base_dy"]), float(g["base_dt"]),
+                                                           dtype=torch.float64, device=DEV)
+    e = 3  # reset(applyNoise=False, fixedInitialValues=...) episode: fully determined without the reference's RNG
+    env = verySimpleAuv.AuvEnv(noiseMagCoeffs=0.1, noiseMagActuation=0.1, currentVelScale=1.0, currentTurbScale=2.0, flow=flow)
+    assert env.action_space.shape == (3,) and env.observation_space.shape == (11,)
+    ob0 = env.reset(applyNoise=False, fixedInitialValues=[np.array([0.3, -0.2]), 1.0, 4.0])
+    env._vec._target[1, 0] = float(g["ep_t_offset"][e])  # the one value the reference drew at random
+    assert np.abs(ob0 - g["ep_obs0"][e]).max() < 1e-14 and env.mMult == 1.0
+    for k in range(g["ep_actions"].shape[1]):
+        ob, r, d, info = env.step(g["ep_actions"][e, k])
+        assert np.abs(ob - g["ep_obs"][e, k]).max() < 1e-9 and abs(r - g["ep_reward"][e, k]) < 1e-8 and info == {}
+        if d:
+            break
+    rows = env.timeHistory if isinstance(env.timeHistory, list) else env.timeHistory.to_dict("records")
+    assert list(rows[0].keys()) == verySimpleAuv.HISTORY_COLUMNS and len(rows[0]) == 40
+    got = np.array([list(r_.values()) for r_ in rows])
+    assert rel_err(got, g["ep_history"][e, :got.shape[0]]) < 1e-8
+    pd = verySimpleAuv.PDController(env.dt)
+    a, _ = pd.predict(ob)
+    assert a.shape == (3,) and np.abs(a).max() <= 1.0
+    assert callable(verySimpleAuv.make_env(0, env_kwargs={"flow": flow}))
+
+
+def test_batched_vs_oracle_auto_reset_sharding_and_fp32():
+    g = load_golden("legacy")
+    n, steps = 512, 40
+    rng = np.random.default_rng(31)
+    acts = rng.uniform(-1, 1, (steps, n, 3))
+    flow64, rflow = make_flows(g)
+    flow32, _ = make_flows(g, torch.float32)
+    kw = dict(noiseMagCoeffs=0.1, noiseMagActuation=0.1, maxSteps=15, auto_reset=True, seed=9)
+    full = AuvVecEnv(n, flow64, dtype=torch.float64, **kw)
+    a = AuvVecEnv(n // 2, flow64, dtype=torch.float64, env_id0=0, **kw)
+    b = AuvVecEnv(n // 2, flow64, dtype=torch.float64, env_id0=n // 2, **kw)
+    e32 = AuvVecEnv(n, flow32, dtype=torch.float32, **kw)
+    ref = o.AuvEnvOracle(n, rflow, noiseMagCoeffs=0.1, noiseMagActuation=0.1, max_steps=15, auto_reset=True, seed=9)
+    r0 = ref.reset()
+    assert np.abs(full.reset().cpu().numpy() - r0).max() < 1e-12
+    a.reset(); b.reset(); e32.reset()
+    assert np.abs(full._mults[:, :n].T.cpu().numpy() - ref.mults).max() < 1e-15
+    n_term, ret = 0, np.zeros(n)
+    for k in range(steps):
+        act = torch.as_tensor(acts[k], device=DEV)
+        obs, rew, done, info = full.step(act)
+        oa, ra, da, _ = a.step(act[: n // 2]); ob, rb, db, _ = b.step(act[n // 2:])
+        assert torch.equal(obs, torch.cat([oa, ob])) and torch.equal(rew, torch.cat([ra, rb])) and torch.equal(done, torch.cat([da, db]))
+        o32, r32, d32, _ = e32.step(act.float())
+        ro, rr, rd, rinfo = ref.step(acts[k])
+        assert np.array_equal(done.cpu().numpy(), rd), k
+        assert np.abs(obs.cpu().numpy() - ro).max() < 1e-9 and np.abs(rew.cpu().numpy() - rr).max() < 1e-8
+        if rd.any():
+            n_term += int(rd.sum())
+            assert np.abs(info["terminal_observation"].cpu().numpy()[rd] - rinfo["terminal_observation"][rd]).max() < 1e-9
+        # fp32: same termination pattern except envs sitting within rounding of a boundary; compare where both agree
+        same = d32.cpu().numpy() == rd
+        assert same.mean() > 0.995
+        if k < 14:  # before the first auto-reset the fp32 trajectories are directly comparable
+            assert np.abs(o32.cpu().numpy() - ro)[same].max() < 1e-4 and np.abs(r32.cpu().numpy() - rr)[same].max() < 2e-3
+    st = full.episode_stats()
+    assert st["episodes"] == n_term and st["nonfinite"] == 0 and st["max_return"] <= 3.0 * 15
