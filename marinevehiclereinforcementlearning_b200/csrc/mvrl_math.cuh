@@ -61,6 +61,17 @@ template <typename T> __device__ __forceinline__ T angle_error(T psi_d, T psi) {
     return a < b ? a : -b;
 }
 
+#ifndef MVRL_POSE_COMP
+#define MVRL_POSE_COMP 1
+#endif
+// y += inc with a Kahan carry (compensated summation across RK4 sub-steps)
+template <typename T> __device__ __forceinline__ void rk4_pose_update(T& y, T& carry, T inc) {
+    const T t = inc - carry;
+    const T s = y + t;
+    carry = (s - y) - t;
+    y = s;
+}
+
 // ---- Philox4x32-10 ---------------------------------------------------------
 struct Philox {
     static __device__ __forceinline__ uint4 run(uint4 c, uint2 k) {

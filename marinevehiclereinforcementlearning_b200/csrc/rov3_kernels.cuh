@@ -172,11 +172,14 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
         }
         derivs3_core(P, sn, cs, s[3], s[4], s[5], rpm, k);
     };
+    // RK4 as in rov6_step_kernel: fp32 pose advanced by the summed increment with a Kahan carry
+    constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
     const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6), h3 = a.h / T(3);
+    T carry[3] = {T(0), T(0), T(0)};
     for (int sub = 0; sub < a.n_sub; ++sub) {
         T k[6], acc[6], yt[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { acc[j] = y[j]; yt[j] = y[j]; }
+        for (int j = 0; j < 6; ++j) { acc[j] = (COMP && j < 3) ? T(0) : y[j]; yt[j] = y[j]; }
 #pragma unroll
         for (int st = 0; st < 4; ++st) {
             f(yt, k, (st & 1) ? hh : T(0));
@@ -189,7 +192,10 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
             }
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) y[j] = acc[j];
+        for (int j = 0; j < 6; ++j) {
+            if (COMP && j < 3) rk4_pose_update(y[j], carry[j], acc[j]);
+            else y[j] = acc[j];
+        }
     }
     y[2] = pymod_pos(y[2], T(MVRL_TWO_PI));  // 3DoF.py:480
     bool bad = false;

@@ -951,5 +951,5 @@ class AuvEnvOracle:
             info["terminal_observation"] = obs.copy()
             self.episode[idx] += np.uint64(1)
             self._install(idx, *self._draw(idx, True))
-            obs = self.observe()
+            obs[idx] = self.observe()[idx]  # only the reset envs: the others keep the obs taken before herr_o / perr_o moved on
         return obs, reward, done, info
