@@ -219,20 +219,15 @@ def run_ours(args, rank, local_rank, world):
     stats = env.episode_stats(reset=True)  # K5; all-reduced over NCCL when world > 1 (off the timed path)
 
     # ---- end to end through the public API with HOST buffers -----------------
+    # BlueROV2Heavy6DoFVecEnv.step_host -> mvrl_rov6_step_host: pinned host [N, 8] actions in, pinned host
+    # obs [N, 9] / reward [N] / done [N] out, every step; upload / step / download pipelined over chunks.
     h_act = [a[:, :n].T.contiguous().cpu().pin_memory() for a in acts[:2]]          # [N, 8] like a VecEnv caller
-    h_obs = torch.empty((n, 9), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
     env._bufs.action = env._action.data_ptr()
 
     def e2e_step(k):
-        obs, rew, done, _ = env.step(h_act[k % 2])          # H2D of [N, 8] + transpose into SoA + fused step
-        h_obs.copy_(obs, non_blocking=True)                  # D2H of obs / reward / done
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(env._done[:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        env.step_host(h_act[k % 2], chunks=args.e2e_chunks)                # returns when the host tensors are complete
 
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 50))
     for k in range(3):
         e2e_step(k)
     barrier()
@@ -247,6 +242,8 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = world * n * e2e_steps / float(t[0])
     h2d = n * 8 * 4
     d2h = n * (9 * 4 + 4 + 1)
+    # launches inside the device-timed region: one fused step kernel per bench step
+    e2e_launches_per_step = 3 * args.e2e_chunks
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -276,7 +273,9 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "inputs larger than L2: ~125 MB touched per step + 4 rotating 32 MiB action batches"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "path": "BlueROV2Heavy6DoFVecEnv.step(pinned host [N,8] actions) -> pinned host obs/reward/done"},
+                        "chunks": args.e2e_chunks, "gpu_launches_per_step": e2e_launches_per_step,
+                        "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
+                                "chunked H2D / transpose / fused step / transpose / D2H pipeline"},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
         print(json.dumps(line))
     if world > 1:
@@ -293,6 +292,7 @@ def main():
     ap.add_argument("--fast-math", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

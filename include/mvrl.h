@@ -156,6 +156,23 @@ MVRL_API int mvrl_rov6_derivs(MvrlRov6* h, int64_t n, int64_t ld, const void* st
 /* One env step for n environments (K1). */
 MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream);
 
+/* Same for the environments [first, first + n) of the buffers only (all arrays keep leading dimension ld;
+ * the Philox stream of environment first + i is that of global id env_id0 + first + i).  Lets host code
+ * build its own copy/compute pipelines over pieces of one batch. */
+MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream);
+
+/* One env step with HOST buffers - the call a host-side VecEnv user makes (BlueROV2Heavy6DoFEnv.step for n
+ * vehicles, 6DoF.py:531-594): actions_host T [n][A] (row = environment) in; obs_host T [n][9], reward_host
+ * T [n] (nullable), done_host [n] (nullable) out.  Pinned host memory is needed for the copies to overlap.
+ * The batch is cut into `chunks` pieces (0: default 4); upload, transpose to SoA, fused step, transpose
+ * back and download of different pieces overlap on streams owned by the handle (PCIe is full duplex).
+ * The whole pipeline is captured into a CUDA graph once per distinct set of pointers (4 cached) and
+ * replayed with one launch; chunks < 0 queues |chunks| pieces directly on the streams instead.
+ * Device staging buffers are allocated on first use.  Starts after the work queued on `stream` and returns
+ * when the host buffers are complete (synchronises `stream`).  b->action is used as the SoA scratch. */
+MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host,
+                                 void* obs_host, void* reward_host, uint8_t* done_host, int chunks, mvrl_stream_t stream);
+
 /* reset(): mask nullable (= all).  initial_setpoint: 6 host doubles or NULL for
  * the random branch (path and target orientation drawn from Philox). */
 MVRL_API int mvrl_rov6_reset(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const uint8_t* mask,

@@ -129,6 +129,23 @@ struct MvrlRov6 {
     bool sp;  // default sparsity pattern holds -> specialised kernels
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
+    // resources of mvrl_rov6_step_host (created on first use, released by destroy)
+    // three queues, one per engine: hs[0] uploads, hs[1] kernels, hs[2] downloads; chunk c flows
+    // hs[0] -ev_up[c]-> hs[1] -ev_k[c]-> hs[2], so no engine ever waits behind another one's backlog
+    static constexpr int kStreams = 3;
+    static constexpr int kMaxChunks = 64;
+    cudaStream_t hs[kStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_out[kStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_up[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
+    void* stage_act = nullptr;   // AoS [n][A] copy of the host actions
+    void* stage_obs = nullptr;   // AoS [n][9] obs ready for download
+    size_t stage_act_bytes = 0, stage_obs_bytes = 0;
+    // the whole host step (copies + kernels over all chunks) captured once per distinct set of
+    // pointers and replayed with a single cudaGraphLaunch
+    static constexpr int kGraphs = 4;
+    struct HostGraph { unsigned long long key[20]; cudaGraphExec_t exec; unsigned long long used; };
+    HostGraph graphs[kGraphs] = {};
+    unsigned long long graph_clock = 0;
 };
 
 template <typename T> static void to_dev(const MvrlRov6Params& p, Rov6Dev<T>& d) {
@@ -206,7 +223,26 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     return MVRL_OK;
 }
 
-extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) { delete h; return MVRL_OK; }
+extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) {
+    if (!h) return MVRL_OK;
+    if (h->hs[0] || h->stage_act || h->stage_obs) {
+        cudaSetDevice(h->c.device);
+        for (int i = 0; i < MvrlRov6::kStreams; ++i) {
+            if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+            if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+        }
+        if (h->ev_in) cudaEventDestroy(h->ev_in);
+        for (int i = 0; i < MvrlRov6::kMaxChunks; ++i) {
+            if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+            if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+        }
+        for (int i = 0; i < MvrlRov6::kGraphs; ++i) if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+        cudaFree(h->stage_act);
+        cudaFree(h->stage_obs);
+    }
+    delete h;
+    return MVRL_OK;
+}
 extern "C" MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h) { return (h && h->sp) ? 1 : 0; }
 
 #define grid_for mvrl_grid_for
@@ -252,36 +288,224 @@ static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, cudaStrea
 }
 
 template <typename T>
-static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t n, int64_t ld, const MvrlRov6Buffers* b, Rov6StepArgs<T>& a) {
+static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, Rov6StepArgs<T>& a) {
+    auto off = [first](void* p) -> T* { return p ? (T*)p + first : nullptr; };
     a.P = P; a.n = n; a.ld = ld;
-    a.state = (T*)b->state; a.action = (const T*)b->action; a.obs = (T*)b->obs; a.reward = (T*)b->reward;
-    a.done = b->done; a.istep = b->istep; a.setpoint = (T*)b->setpoint; a.path = (T*)b->path; a.ctrl = (T*)b->ctrl;
-    a.episode = b->episode; a.term_obs = (T*)b->terminal_obs; a.aux = (T*)b->aux; a.stats = b->ep_stats;
+    a.state = off(b->state); a.action = off(b->action); a.obs = off(b->obs); a.reward = off(b->reward);
+    a.done = b->done + first; a.istep = b->istep + first; a.setpoint = off(b->setpoint); a.path = off(b->path); a.ctrl = off(b->ctrl);
+    a.episode = b->episode ? b->episode + first : nullptr; a.term_obs = off(b->terminal_obs); a.aux = off(b->aux); a.stats = b->ep_stats;
     a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub);
     a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
-    a.seed = h->c.seed; a.env_id0 = h->c.env_id0;
+    a.seed = h->c.seed; a.env_id0 = h->c.env_id0 + (unsigned long long)first;
     a.auto_reset = h->c.auto_reset; a.fixed_sp = h->c.fixed_sp;
 }
 
-extern "C" MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
-    if (!h || !b) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: null argument");
-    if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: need 0 <= n <= ld (n=%lld ld=%lld)", (long long)n, (long long)ld);
+static int check_step_args(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const char* who) {
+    if (!h || !b) return mvrl_fail(MVRL_EINVAL, "%s: null argument", who);
+    if (first < 0 || n < 0 || ld < first + n) return mvrl_fail(MVRL_EINVAL, "%s: need 0 <= first, 0 <= n, first + n <= ld (first=%lld n=%lld ld=%lld)", who, (long long)first, (long long)n, (long long)ld);
     if (!b->state || !b->action || !b->obs || !b->reward || !b->done || !b->istep || !b->setpoint || !b->path)
-        return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: state/action/obs/reward/done/istep/setpoint/path are required");
-    if (h->c.action_mode == MVRL_ACT_SETPOINT && !b->ctrl) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: ctrl is required in set-point mode");
-    if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step: episode is required with auto_reset");
-    if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
-    cudaStream_t s = (cudaStream_t)stream;
+        return mvrl_fail(MVRL_EINVAL, "%s: state/action/obs/reward/done/istep/setpoint/path are required", who);
+    if (h->c.action_mode == MVRL_ACT_SETPOINT && !b->ctrl) return mvrl_fail(MVRL_EINVAL, "%s: ctrl is required in set-point mode", who);
+    if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "%s: episode is required with auto_reset", who);
+    return MVRL_OK;
+}
+
+// launches the fused step for environments [first, first + n) on stream s
+static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, cudaStream_t s) {
     if (h->c.dtype == MVRL_F64) {
-        Rov6StepArgs<double> a; fill_step_args(h, h->pd, n, ld, b, a);
+        Rov6StepArgs<double> a; fill_step_args(h, h->pd, first, n, ld, b, a);
         dispatch_step<double, false>(a, h->c.action_mode, h->sp, s);
     } else {
-        Rov6StepArgs<float> a; fill_step_args(h, h->pf, n, ld, b, a);
+        Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
         if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, s);
         else dispatch_step<float, false>(a, h->c.action_mode, h->sp, s);
     }
+}
+
+extern "C" MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
+    { const int rc = check_step_args(h, 0, n, ld, b, "mvrl_rov6_step"); if (rc != MVRL_OK) return rc; }
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    launch_step_range(h, 0, n, ld, b, (cudaStream_t)stream);
     return check_launch("rov6_step");
+}
+
+extern "C" MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
+    { const int rc = check_step_args(h, first, n, ld, b, "mvrl_rov6_step_range"); if (rc != MVRL_OK) return rc; }
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    launch_step_range(h, first, n, ld, b, (cudaStream_t)stream);
+    return check_launch("rov6_step_range");
+}
+
+// ---------------------------------------------------------------------------
+// step with HOST buffers: chunked upload / transpose / step / transpose / download pipeline
+// ---------------------------------------------------------------------------
+// AoS [n][K] (row = environment, the layout a host-side VecEnv caller holds) <-> SoA [K][ld].
+// Tiles of 32 environments go through shared memory so that both sides are coalesced.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(long n, long ld, const T* __restrict__ aos, T* __restrict__ soa) {
+    constexpr int KP = K | 1;  // odd row pitch: conflict-free column reads
+    __shared__ T tile[256 * KP];
+    const long base = (long)blockIdx.x * 256;
+    const int cnt = (int)((n - base) < 256 ? (n - base) : 256);
+    for (int e = threadIdx.x; e < cnt * K; e += 256) tile[(e / K) * KP + (e % K)] = aos[base * K + e];
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) soa[k * ld + base + threadIdx.x] = tile[threadIdx.x * KP + k];
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(long n, long ld, const T* __restrict__ soa, T* __restrict__ aos) {
+    constexpr int KP = K | 1;
+    __shared__ T tile[256 * KP];
+    const long base = (long)blockIdx.x * 256;
+    const int cnt = (int)((n - base) < 256 ? (n - base) : 256);
+    if ((int)threadIdx.x < cnt) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) tile[threadIdx.x * KP + k] = soa[k * ld + base + threadIdx.x];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * K; e += 256) aos[base * K + e] = tile[(e / K) * KP + (e % K)];
+}
+
+template <typename T>
+static void launch_transposes_in(int n_act, long n, long ld, const T* aos, T* soa, cudaStream_t s) {
+    const unsigned g = grid_for(n, 256);
+    if (n_act == 8) aos_to_soa_kernel<T, 8><<<g, 256, 0, s>>>(n, ld, aos, soa);
+    else aos_to_soa_kernel<T, 6><<<g, 256, 0, s>>>(n, ld, aos, soa);
+}
+
+static int ensure_host_pipeline(MvrlRov6* h, size_t act_bytes, size_t obs_bytes) {
+    if (!h->hs[0]) {
+        for (int i = 0; i < MvrlRov6::kStreams; ++i) {
+            MVRL_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+            MVRL_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+        MVRL_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        for (int i = 0; i < MvrlRov6::kMaxChunks; ++i) {
+            MVRL_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+            MVRL_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    if (h->stage_act_bytes < act_bytes) {
+        if (h->stage_act) MVRL_CUDA(cudaFree(h->stage_act));
+        h->stage_act = nullptr; h->stage_act_bytes = 0;
+        MVRL_CUDA(cudaMalloc(&h->stage_act, act_bytes));
+        h->stage_act_bytes = act_bytes;
+    }
+    if (h->stage_obs_bytes < obs_bytes) {
+        if (h->stage_obs) MVRL_CUDA(cudaFree(h->stage_obs));
+        h->stage_obs = nullptr; h->stage_obs_bytes = 0;
+        MVRL_CUDA(cudaMalloc(&h->stage_obs, obs_bytes));
+        h->stage_obs_bytes = obs_bytes;
+    }
+    return MVRL_OK;
+}
+
+static void drop_host_graphs(MvrlRov6* h) {
+    for (int i = 0; i < MvrlRov6::kGraphs; ++i) {
+        if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+        h->graphs[i] = MvrlRov6::HostGraph{};
+    }
+}
+
+// queues the chunked pipeline: everything is ordered after `root` and joined back into `root`
+static int enqueue_host_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host, void* obs_host,
+                             void* reward_host, uint8_t* done_host, int chunks, cudaStream_t root) {
+    const size_t es = h->c.dtype == MVRL_F64 ? 8 : 4;
+    const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;
+    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;   // multiple of the transpose tile
+    MVRL_CUDA(cudaEventRecord(h->ev_in, root));
+    for (int i = 0; i < MvrlRov6::kStreams; ++i) MVRL_CUDA(cudaStreamWaitEvent(h->hs[i], h->ev_in, 0));
+    cudaStream_t s_up = h->hs[0], s_k = h->hs[1], s_dn = h->hs[2];
+    int c = 0;
+    for (int64_t first = 0; first < n; first += per, ++c) {
+        const int64_t cnt = (n - first) < per ? (n - first) : per;
+        char* d_act = (char*)h->stage_act + (size_t)first * n_act * es;
+        char* d_obs = (char*)h->stage_obs + (size_t)first * 9 * es;
+        MVRL_CUDA(cudaMemcpyAsync(d_act, (const char*)actions_host + (size_t)first * n_act * es, (size_t)cnt * n_act * es, cudaMemcpyHostToDevice, s_up));
+        MVRL_CUDA(cudaEventRecord(h->ev_up[c], s_up));
+        MVRL_CUDA(cudaStreamWaitEvent(s_k, h->ev_up[c], 0));
+        if (es == 8) launch_transposes_in<double>(n_act, cnt, ld, (const double*)d_act, (double*)b->action + first, s_k);
+        else launch_transposes_in<float>(n_act, cnt, ld, (const float*)d_act, (float*)b->action + first, s_k);
+        launch_step_range(h, first, cnt, ld, b, s_k);
+        if (es == 8) soa_to_aos_kernel<double, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const double*)b->obs + first, (double*)d_obs);
+        else soa_to_aos_kernel<float, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const float*)b->obs + first, (float*)d_obs);
+        MVRL_CUDA(cudaEventRecord(h->ev_k[c], s_k));
+        MVRL_CUDA(cudaStreamWaitEvent(s_dn, h->ev_k[c], 0));
+        MVRL_CUDA(cudaMemcpyAsync((char*)obs_host + (size_t)first * 9 * es, d_obs, (size_t)cnt * 9 * es, cudaMemcpyDeviceToHost, s_dn));
+        if (reward_host) MVRL_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)first * es, (const char*)b->reward + (size_t)first * es, (size_t)cnt * es, cudaMemcpyDeviceToHost, s_dn));
+        if (done_host) MVRL_CUDA(cudaMemcpyAsync(done_host + first, b->done + first, (size_t)cnt, cudaMemcpyDeviceToHost, s_dn));
+    }
+    { const int rc = check_launch("rov6_step_host"); if (rc != MVRL_OK) return rc; }
+    for (int i = 0; i < MvrlRov6::kStreams; ++i) {
+        MVRL_CUDA(cudaEventRecord(h->ev_out[i], h->hs[i]));
+        MVRL_CUDA(cudaStreamWaitEvent(root, h->ev_out[i], 0));
+    }
+    return MVRL_OK;
+}
+
+extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host,
+                                            void* obs_host, void* reward_host, uint8_t* done_host, int chunks, mvrl_stream_t stream) {
+    { const int rc = check_step_args(h, 0, n, ld, b, "mvrl_rov6_step_host"); if (rc != MVRL_OK) return rc; }
+    if (!actions_host || !obs_host) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step_host: actions_host and obs_host are required");
+    if (n == 0) return MVRL_OK;
+    MVRL_CUDA(cudaSetDevice(h->c.device));
+    const size_t es = h->c.dtype == MVRL_F64 ? 8 : 4;
+    const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;
+    const size_t need_act = (size_t)n * n_act * es, need_obs = (size_t)n * 9 * es;
+    if (h->stage_act_bytes < need_act || h->stage_obs_bytes < need_obs) drop_host_graphs(h);  // they hold the old staging pointers
+    { const int rc = ensure_host_pipeline(h, need_act, need_obs); if (rc != MVRL_OK) return rc; }
+    const bool graph_mode = chunks >= 0;   // chunks < 0: |chunks| pieces queued directly on the streams (no graph)
+    if (chunks == 0) chunks = 4;
+    if (chunks < 0) chunks = -chunks;
+    if (chunks > MvrlRov6::kMaxChunks) chunks = MvrlRov6::kMaxChunks;
+    cudaStream_t user = (cudaStream_t)stream;
+    if (!graph_mode) {
+        { const int rc = enqueue_host_step(h, n, ld, b, actions_host, obs_host, reward_host, done_host, chunks, user); if (rc != MVRL_OK) return rc; }
+        MVRL_CUDA(cudaStreamSynchronize(user));
+        return MVRL_OK;
+    }
+    // everything a captured graph bakes in
+    unsigned long long key[20] = {(unsigned long long)n, (unsigned long long)ld, (unsigned long long)chunks,
+        (unsigned long long)actions_host, (unsigned long long)obs_host, (unsigned long long)reward_host, (unsigned long long)done_host,
+        (unsigned long long)b->state, (unsigned long long)b->action, (unsigned long long)b->obs, (unsigned long long)b->reward,
+        (unsigned long long)b->done, (unsigned long long)b->istep, (unsigned long long)b->setpoint, (unsigned long long)b->path,
+        (unsigned long long)b->ctrl, (unsigned long long)b->episode, (unsigned long long)b->terminal_obs, (unsigned long long)b->aux,
+        (unsigned long long)b->ep_stats};
+    MvrlRov6::HostGraph* g = nullptr;
+    MvrlRov6::HostGraph* lru = &h->graphs[0];
+    for (int i = 0; i < MvrlRov6::kGraphs; ++i) {
+        MvrlRov6::HostGraph* e = &h->graphs[i];
+        if (e->exec && memcmp(e->key, key, sizeof(key)) == 0) { g = e; break; }
+        if (e->used < lru->used) lru = e;
+    }
+    if (!g) {
+        g = lru;
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        MVRL_CUDA(cudaStreamBeginCapture(h->hs[0], cudaStreamCaptureModeThreadLocal));
+        // hs[0] is the capture origin: the other streams fork from it and join back
+        int rc = MVRL_OK;
+        {
+            // temporarily treat hs[0] as `root`; chunk streams are hs[1..] plus hs[0] itself
+            rc = enqueue_host_step(h, n, ld, b, actions_host, obs_host, reward_host, done_host, chunks, h->hs[0]);
+        }
+        cudaError_t ce = cudaStreamEndCapture(h->hs[0], &graph);
+        if (rc != MVRL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return mvrl_fail(MVRL_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { g->exec = nullptr; return mvrl_fail(MVRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+        memcpy(g->key, key, sizeof(key));
+    }
+    g->used = ++h->graph_clock;
+    MVRL_CUDA(cudaGraphLaunch(g->exec, user));
+    MVRL_CUDA(cudaStreamSynchronize(user));   // the host buffers are valid when this returns
+    return MVRL_OK;
 }
 
 // ---------------------------------------------------------------------------

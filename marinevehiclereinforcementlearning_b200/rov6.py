@@ -336,6 +336,40 @@ class _RovVecEnv:
             infos["terminal_observation"] = self._terminal_obs[:, :n].T
         return self.state, self._reward[:n], self._done[:n].bool(), infos
 
+    def step_host(self, actions, obs_out=None, reward_out=None, done_out=None, chunks=4):
+        """One env step for a caller that lives on the HOST: ``actions`` is a CPU tensor
+        ``[N, A]`` (pinned memory lets the copies overlap), results land in CPU tensors
+        ``obs [N, obs]``, ``reward [N]``, ``done [N]`` (uint8), allocated pinned on first use.
+        Runs ``mvrl_rov6_step_host``: upload, SoA transpose, fused step, transpose back and
+        download are pipelined over ``chunks`` pieces of the batch.  Returns when the host
+        tensors are complete."""
+        if self.HANDLE.PREFIX != "mvrl_rov6":
+            raise NotImplementedError("step_host / step_range are implemented for the 6DoF env")
+        n = self.num_envs
+        if actions.device.type != "cpu" or actions.dtype != self.dtype or tuple(actions.shape) != (n, self.lenAction) or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous CPU tensor [%d, %d] of %s" % (n, self.lenAction, self.dtype))
+        if obs_out is None:
+            if getattr(self, "_h_obs", None) is None:
+                self._h_obs = torch.empty((n, self.lenObs), dtype=self.dtype).pin_memory()
+                self._h_reward = torch.empty(n, dtype=self.dtype).pin_memory()
+                self._h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+            obs_out, reward_out, done_out = self._h_obs, self._h_reward, self._h_done
+        h = self._get_handle()
+        self._bufs.action = self._action.data_ptr()
+        _lib.check(h.lib.mvrl_rov6_step_host(h._h, n, self.ld, C.byref(self._bufs), C.c_void_p(actions.data_ptr()),
+                                             C.c_void_p(obs_out.data_ptr()),
+                                             None if reward_out is None else C.c_void_p(reward_out.data_ptr()),
+                                             None if done_out is None else C.c_void_p(done_out.data_ptr()),
+                                             int(chunks), _lib.current_stream(self.device)))
+        return obs_out, reward_out, done_out
+
+    def step_range_async(self, first, count):
+        """Launch the fused step for environments ``[first, first + count)`` only (``mvrl_rov6_step_range``)."""
+        if self.HANDLE.PREFIX != "mvrl_rov6":
+            raise NotImplementedError("step_host / step_range are implemented for the 6DoF env")
+        h = self._get_handle()
+        _lib.check(h.lib.mvrl_rov6_step_range(h._h, int(first), int(count), self.ld, C.byref(self._bufs), _lib.current_stream(self.device)))
+
     def observe(self):
         """dataToState for the current device state (6DoF.py:467-483 / 3DoF.py:397-409),
         [N, obs]: resources.angleError / clip run on the device through torch views of the

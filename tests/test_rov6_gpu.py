@@ -287,3 +287,25 @@ def test_resources_helpers():
     assert np.abs(res.coordinateTransform(a[:, 0], a[:, 1], a[:, 2], dof=3) - r["ct_J3"]).max() < 1e-15
     assert res.coordinateTransform(0.1, 0.2, 0.3, dof=6).shape == (6, 6)
     assert res.coordinateTransform(0.1, 0.2, 0.3).shape == (3, 3)
+
+
+def test_step_host_and_step_range_match_step_bitwise():
+    """The host-buffer pipeline (chunked upload / transpose / step / download) and the range launch
+    give exactly what one whole-batch launch gives, including auto-reset draws (global env ids)."""
+    n, steps = 5000, 7   # not a multiple of the chunk or tile size
+    for dtype, mode, na in ((torch.float32, "rpm", 8), (torch.float64, "setpoint", 6)):
+        rng = np.random.default_rng(41)
+        scale = 3500.0 if mode == "rpm" else 1.0
+        acts = torch.as_tensor(rng.uniform(-scale, scale, (steps, n, na)), dtype=dtype)
+        kw = dict(action_mode=mode, dtype=dtype, device=DEV, maxSteps=3, auto_reset=True, seed=5)
+        a, b, c = (BlueROV2Heavy6DoFVecEnv(n, **kw) for _ in range(3))
+        a.reset(); b.reset(); c.reset()
+        for k in range(steps):
+            obs, rew, done, _ = a.step(acts[k].to(DEV))
+            h_obs, h_rew, h_done = b.step_host(acts[k].pin_memory(), chunks=3 if k % 2 else -3)  # CUDA-graph replay / direct streams
+            c.set_actions(acts[k].to(DEV))
+            for first in range(0, n, 1111):
+                c.step_range_async(first, min(1111, n - first))
+            assert torch.equal(obs.cpu(), h_obs) and torch.equal(rew.cpu(), h_rew) and torch.equal(done.cpu(), h_done.bool())
+            assert torch.equal(a._state, b._state) and torch.equal(a._state, c._state) and torch.equal(a._obs, c._obs)
+            assert torch.equal(a._path, b._path) and torch.equal(a._path, c._path)
