@@ -40,11 +40,29 @@ MAX_STEPS = 250
 FLOP_PER_ENV_STEP = 1600 * N_SUB + 60          # FMA = 2, other fp ops = 1, libm calls not counted
 BYTES_PER_ENV_STEP_F32 = 177                   # state r/w, action r, obs/reward/done w, counter r/w
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+NCU_TRAFFIC_BYTES = 183.1e6                    # measured DRAM bytes of one 1 Mi-env launch (profiles/r1_e_x2_ncu_full_summary.txt)
 
 
-def workload_name(envs):
-    return ("rov6_step fp32: BlueROV2 Heavy 6DoF, %d envs/GPU, rpm actions U(-3500,3500), dt=%.1f as nSub=%d RK4, "
-            "maxSteps=%d auto-reset" % (envs, DT, N_SUB, MAX_STEPS))
+ACTION_SCALE = {"rpm": 3500.0, "force": 40.0, "setpoint": 1.0}
+ACTION_DIM = {"rpm": 8, "force": 6, "setpoint": 6}
+# derivative = 360 flop (rpm) / 610 (PID set-point; force mode has the allocation but no PID: 538)
+DERIV_FLOP = {"rpm": 360, "force": 538, "setpoint": 610}
+
+
+def flop_per_env_step(mode, n_sub):
+    return (4 * DERIV_FLOP[mode] + 160) * n_sub + 60
+
+
+def bytes_per_env_step(mode, w):
+    b = 12 * w * 2 + ACTION_DIM[mode] * w + 9 * w + w + 1 + 8          # state r/w, action r, obs/reward/done w, counter r/w
+    if mode == "setpoint":
+        b += 13 * w * 2 + 6 * w * 2 + 6 * w                            # PID state r/w, set-point r/w, path r
+    return b
+
+
+def workload_name(envs, mode="rpm", dtype="f32", n_sub=N_SUB):
+    return ("rov6_step %s: BlueROV2 Heavy 6DoF, %d envs/GPU, %s actions U(-%g,%g), dt=%.1f as nSub=%d RK4, "
+            "maxSteps=%d auto-reset" % (dtype, envs, mode, ACTION_SCALE[mode], ACTION_SCALE[mode], DT, n_sub, MAX_STEPS))
 
 
 # --------------------------------------------------------------------------
@@ -174,13 +192,17 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
-    env = BlueROV2Heavy6DoFVecEnv(n, action_mode="rpm", dtype=torch.float32, device=dev, dt=DT, maxSteps=MAX_STEPS, n_sub=N_SUB,
+    mode, n_sub = args.action_mode, args.n_sub
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if args.dtype == "f64" else 4
+    na = ACTION_DIM[mode]
+    env = BlueROV2Heavy6DoFVecEnv(n, action_mode=mode, dtype=tdtype, device=dev, dt=DT, maxSteps=args.max_steps, n_sub=n_sub,
                                   seed=1234, env_id0=rank * n, auto_reset=True, fast_math=bool(args.fast_math),
-                                  record_terminal_obs=False)
+                                  record_terminal_obs=False, collect_stats=not args.no_stats)
     env.reset()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4  # rotating action batches: 4 x 32 MiB on top of 125 MB touched per step > 126 MB L2
-    acts = [(torch.rand((8, env.ld), generator=gen, device=dev, dtype=torch.float32) * 2 - 1) * 3500.0 for _ in range(n_act)]
+    acts = [(torch.rand((na, env.ld), generator=gen, device=dev, dtype=tdtype) * 2 - 1) * ACTION_SCALE[mode] for _ in range(n_act)]
     # stagger episode phase like a long-running job: env i starts at iStep = i % maxSteps
     env._istep.copy_((torch.arange(env.ld, device=dev) % MAX_STEPS).to(torch.int32))
 
@@ -196,6 +218,18 @@ def run_ours(args, rank, local_rank, world):
     for k in range(args.warmup):
         one_step(k)
     barrier()
+    graph = None
+    if args.graph:  # replay the K timed launches as one CUDA graph (no per-launch host cost)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for k in range(args.steps):
+                    one_step(k)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph.replay()   # warm-up replay
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -203,8 +237,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     t0 = time.time()
     e0.record()
-    for k in range(args.steps):
-        one_step(k)
+    if graph is not None:
+        graph.replay()
+    else:
+        for k in range(args.steps):
+            one_step(k)
     e1.record()
     barrier()
     t1 = time.time()
@@ -216,12 +253,12 @@ def run_ours(args, rank, local_rank, world):
     ms = float(t[0])
     value = world * n * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
-    stats = env.episode_stats(reset=True)  # K5; all-reduced over NCCL when world > 1 (off the timed path)
+    stats = None if args.no_stats else env.episode_stats(reset=True)  # K5; all-reduced over NCCL when world > 1 (off the timed path)
 
     # ---- end to end through the public API with HOST buffers -----------------
     # BlueROV2Heavy6DoFVecEnv.step_host -> mvrl_rov6_step_host: pinned host [N, 8] actions in, pinned host
     # obs [N, 9] / reward [N] / done [N] out, every step; upload / step / download pipelined over chunks.
-    h_act = [a[:, :n].T.contiguous().cpu().pin_memory() for a in acts[:2]]          # [N, 8] like a VecEnv caller
+    h_act = [a[:, :n].T.contiguous().cpu().pin_memory() for a in acts[:2]]          # [N, A] like a VecEnv caller
     env._bufs.action = env._action.data_ptr()
 
     def e2e_step(k):
@@ -240,8 +277,8 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t[0])
-    h2d = n * 8 * 4
-    d2h = n * (9 * 4 + 4 + 1)
+    h2d = n * na * w
+    d2h = n * (9 * w + w + 1)
     # launches inside the device-timed region: one fused step kernel per bench step
     e2e_launches_per_step = 3 * args.e2e_chunks
 
@@ -250,14 +287,19 @@ def run_ours(args, rank, local_rank, world):
         fp32_peak = _lib.measure_fma_peak(_lib.F32, local_rank)   # K6, measured now on this GPU
         fp64_peak = _lib.measure_fma_peak(_lib.F64, local_rank, iters=1024)
         per_gpu_rate = n / (ms_per_step * 1e-3)
-        ach_tflops = per_gpu_rate * FLOP_PER_ENV_STEP / 1e12
-        ach_gbs = per_gpu_rate * BYTES_PER_ENV_STEP_F32 / 1e9
-        roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak,
-                    "traffic": None, "peak_source": "FP32 FMA-chain microbenchmark (mvrl_measure_fma_peak) run on this GPU in this process; "
-                    "nominal %.1f" % NOMINAL_FP32_TFLOPS, "fp64_peak_tflops": fp64_peak,
-                    "flop_per_env_step": FLOP_PER_ENV_STEP,
+        flop, nbytes = flop_per_env_step(mode, n_sub), bytes_per_env_step(mode, w)
+        ach_tflops = per_gpu_rate * flop / 1e12
+        ach_gbs = per_gpu_rate * nbytes / 1e9
+        fp_peak = fp64_peak if args.dtype == "f64" else fp32_peak
+        roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tflops, "peak": fp_peak, "unit": "TFLOP/s",
+                    "frac": ach_tflops / fp_peak, "traffic": NCU_TRAFFIC_BYTES if (mode, args.dtype, n_sub, n) == ("rpm", "f32", N_SUB, ENVS_PER_GPU) else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rov6_step launch, ncu --set full, profiles/r1_e_*",
+                    "peak_source": "FMA-chain microbenchmark (mvrl_measure_fma_peak: operands from uniform registers) run on this GPU in this "
+                    "process; nominal fp32 %.1f. With three distinct register operands FFMA sustains only 0.61 inst/clk/SMSP "
+                    "(45.7 TFLOP/s, tools/ffma_regs.cu)" % NOMINAL_FP32_TFLOPS,
+                    "fp32_peak_tflops": fp32_peak, "fp64_peak_tflops": fp64_peak, "flop_per_env_step": flop,
                     "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
-                            "bytes_per_env_step": BYTES_PER_ENV_STEP_F32, "peak_source": peak_src}}
+                            "bytes_per_env_step": nbytes, "peak_source": peak_src}}
         cpu = None
         if not args.no_cpu:
             rate, secs, used = cpu_port_rate(32768, args.cpu_steps)
@@ -267,9 +309,10 @@ def run_ours(args, rank, local_rank, world):
                    "python_port_one_core": python_port_rate(2.0)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(n), "envs_per_gpu": n, "envs_total": n * world, "n_sub": N_SUB,
-                           "action_mode": "rpm", "fast_math": bool(args.fast_math), "parallelism": "env-sharded x%d, no collective on the step path" % world,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": workload_name(n, mode, args.dtype, n_sub), "envs_per_gpu": n, "envs_total": n * world, "n_sub": n_sub,
+                           "action_mode": mode, "fast_math": bool(args.fast_math), "cuda_graph": bool(args.graph),
+                           "two_envs_per_thread_ffma2": os.environ.get("MVRL_NO_X2", "0") != "1" and args.dtype == "f32", "parallelism": "env-sharded x%d, no collective on the step path" % world,
                            "l2": "inputs larger than L2: ~125 MB touched per step + 4 rotating 32 MiB action batches"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -293,6 +336,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--action-mode", default="rpm", choices=["rpm", "force", "setpoint"], help="default rpm = BASELINE config 3")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--n-sub", type=int, default=N_SUB)
+    ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
+    ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
+    ap.add_argument("--no-stats", action="store_true", help="diagnostics: do not accumulate episode statistics in the step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

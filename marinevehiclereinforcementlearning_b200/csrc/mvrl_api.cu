@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -127,6 +128,7 @@ struct MvrlRov6 {
     MvrlRov6Params p;
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
+    bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
     // resources of mvrl_rov6_step_host (created on first use, released by destroy)
@@ -217,6 +219,7 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->p = *params;
     h->c = *cfg;
     h->sp = default_sparsity(*params);
+    { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
     to_dev(*params, h->pf);
     to_dev(*params, h->pd);
     *out = h;
@@ -269,21 +272,35 @@ int mvrl_require_device(int device) {
 #endif
 #define MVRL_STAGE_UNROLL(T) (sizeof(T) == 4 ? MVRL_STAGE_UNROLL_F32 : MVRL_STAGE_UNROLL_F64)
 
+// Two fp32 environments per thread (packed FFMA2 path) need 8-byte aligned rows.
+template <typename T> static bool x2_layout_ok(const Rov6StepArgs<T>& a) {
+    if (sizeof(T) != 4 || (a.ld & 1)) return false;
+    const void* ptrs[] = {a.state, a.action, a.obs, a.reward, a.setpoint, a.path, a.ctrl};
+    for (const void* p : ptrs) if (((uintptr_t)p) & 7u) return false;
+    return true;
+}
+
 template <typename T, int MODE, bool SP, bool FAST>
-static void launch_step(const Rov6StepArgs<T>& a, cudaStream_t s) {
+static void launch_step(const Rov6StepArgs<T>& a, bool x2, cudaStream_t s) {
     // the four RK4 stages are unrolled: measured faster than the rolled loop (r1 profile notes)
     constexpr int UNROLL = MVRL_STAGE_UNROLL(T);
+    if constexpr (sizeof(T) == 4) {
+        if (x2 && x2_layout_ok(a)) {
+            rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for((a.n + 1) / 2, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
+            return;
+        }
+    }
     rov6_step_kernel<T, MODE, SP, FAST, UNROLL><<<grid_for(a.n, MVRL_STEP_BLOCK), MVRL_STEP_BLOCK, 0, s>>>(a);
 }
 template <typename T, bool FAST>
-static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, cudaStream_t s) {
+static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, bool x2, cudaStream_t s) {
     switch (mode * 2 + (sp ? 1 : 0)) {
-        case 0: launch_step<T, ACT_RPM, false, FAST>(a, s); break;
-        case 1: launch_step<T, ACT_RPM, true, FAST>(a, s); break;
-        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, s); break;
-        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, s); break;
-        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, s); break;
-        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, s); break;
+        case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, s); break;
+        case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, s); break;
+        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, x2, s); break;
+        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, x2, s); break;
+        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, x2, s); break;
+        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, x2, s); break;
     }
 }
 
@@ -314,11 +331,11 @@ static int check_step_args(const MvrlRov6* h, int64_t first, int64_t n, int64_t 
 static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, cudaStream_t s) {
     if (h->c.dtype == MVRL_F64) {
         Rov6StepArgs<double> a; fill_step_args(h, h->pd, first, n, ld, b, a);
-        dispatch_step<double, false>(a, h->c.action_mode, h->sp, s);
+        dispatch_step<double, false>(a, h->c.action_mode, h->sp, false, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
-        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, s);
-        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, s);
+        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, h->x2, s);
+        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, h->x2, s);
     }
 }
 

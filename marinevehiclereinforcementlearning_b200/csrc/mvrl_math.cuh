@@ -39,31 +39,100 @@ template <typename T> __device__ __forceinline__ bool finite_t(T x);
 template <> __device__ __forceinline__ bool finite_t<double>(double x) { return isfinite(x); }
 template <> __device__ __forceinline__ bool finite_t<float>(float x) { return isfinite(x); }
 
+// ---- value types ----------------------------------------------------------
+// The model code is written once over a value type V: float / double carry one
+// environment per thread; F2 carries TWO fp32 environments per thread in a
+// register pair and maps +, *, fma onto the packed FFMA2 / FADD2 / FMUL2
+// instructions of sm_100 (two FMAs per lane per issue slot; scalar and uniform
+// operands broadcast for free, neg / abs are operand modifiers).  The step
+// kernels are issue-bound, not pipe-bound, so halving the issue slots of the
+// FP work is a direct speed-up (profiles/ r1 notes).
+struct F2 {
+    float2 v;
+    __device__ __forceinline__ F2() {}
+    __device__ __forceinline__ F2(float a) { v = make_float2(a, a); }
+    __device__ __forceinline__ F2(float a, float b) { v = make_float2(a, b); }
+};
+__device__ __forceinline__ F2 f2_from(float2 q) { F2 r; r.v = q; return r; }
+__device__ __forceinline__ F2 operator-(F2 a) { return F2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return f2_from(__fadd2_rn(a.v, b.v)); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return f2_from(__fadd2_rn(a.v, (-b).v)); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return f2_from(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ F2& operator+=(F2& a, F2 b) { a = a + b; return a; }
+__device__ __forceinline__ F2 fmaf_t(F2 a, F2 b, F2 c) { return f2_from(__ffma2_rn(a.v, b.v, c.v)); }
+__device__ __forceinline__ F2 tabs(F2 a) { return F2(fabsf(a.v.x), fabsf(a.v.y)); }
+__device__ __forceinline__ F2 tmin(F2 a, F2 b) { return F2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y)); }
+__device__ __forceinline__ F2 tmax(F2 a, F2 b) { return F2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y)); }
+
+template <typename V> struct VT { using S = V; static constexpr int L = 1; };
+template <> struct VT<F2> { using S = float; static constexpr int L = 2; };
+
+// lane access (l is a compile-time constant after unrolling)
+template <typename V> __device__ __forceinline__ V lane_get(V v, int) { return v; }
+__device__ __forceinline__ float lane_get(F2 v, int l) { return l == 0 ? v.v.x : v.v.y; }
+template <typename V> __device__ __forceinline__ void lane_set(V& v, int, V x) { v = x; }
+__device__ __forceinline__ void lane_set(F2& v, int l, float x) { if (l == 0) v.v.x = x; else v.v.y = x; }
+
+// comparisons / selects: bool for one environment, a pair of predicates for two
+struct B2 { bool x, y; };
+template <typename T> __device__ __forceinline__ bool vlt(T a, T b) { return a < b; }
+__device__ __forceinline__ B2 vlt(F2 a, F2 b) { return B2{a.v.x < b.v.x, a.v.y < b.v.y}; }
+template <typename T> __device__ __forceinline__ bool vgt(T a, T b) { return a > b; }
+__device__ __forceinline__ B2 vgt(F2 a, F2 b) { return B2{a.v.x > b.v.x, a.v.y > b.v.y}; }
+template <typename T> __device__ __forceinline__ bool visnan(T a) { return a != a; }
+__device__ __forceinline__ B2 visnan(F2 a) { return B2{a.v.x != a.v.x, a.v.y != a.v.y}; }
+template <typename T> __device__ __forceinline__ T vsel(bool m, T a, T b) { return m ? a : b; }
+__device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) { return F2(m.x ? a.v.x : b.v.x, m.y ? a.v.y : b.v.y); }
+__device__ __forceinline__ bool vany(bool m) { return m; }
+__device__ __forceinline__ bool vany(B2 m) { return m.x || m.y; }
+__device__ __forceinline__ float vcopysign(float mag, float sign) { return copysignf(mag, sign); }
+__device__ __forceinline__ double vcopysign(double mag, double sign) { return copysign(mag, sign); }
+__device__ __forceinline__ F2 vcopysign(F2 mag, F2 sign) { return F2(copysignf(mag.v.x, sign.v.x), copysignf(mag.v.y, sign.v.y)); }
+
 #define MVRL_TWO_PI 6.283185307179586476925286766559
 
 // Python's float `%` (== numpy.mod): result takes the divisor's sign, and an
 // exact zero remainder is +0 for a positive divisor.  The reference wraps
 // angles with it (dynamicsModel_BlueROV2_Heavy_6DoF.py:560, resources.py:92-93).
-template <typename T> __device__ __forceinline__ T pymod_pos(T a, T b) {  // b > 0
-    T r;
-    if (tabs(a) < b) r = a;  // fmod is the identity here; skips the slow path
-    else r = Real<T>::fmod(a, b);
+// |a| < b (the overwhelmingly common case for wrapped angles): no fmod, no branch.
+template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) { return a < T(0) ? a + b : tabs(a); }
+// general case, kept out of line: libm's fmod carries a long slow path that would otherwise be
+// inlined at every call site of the step kernels (measured: instruction-fetch stalls in the epilogue)
+template <typename T> __device__ __noinline__ T pymod_general(T a, T b) {
+    T r = Real<T>::fmod(a, b);
     if (r != T(0)) { if (r < T(0)) r += b; }
     else r = T(0);
     return r;
 }
+template <typename T> __device__ __forceinline__ T pymod_pos(T a, T b) {  // b > 0
+    if (tabs(a) < b) return pymod_small(a, b);
+    return pymod_general(a, b);
+}
 
-// resources.angleError (resources.py:75-95)
+// resources.angleError (resources.py:75-95): a = (psi_d - psi) % 2pi, b = (psi - psi_d) % 2pi, a if a < b else -b
+template <typename T> __device__ __forceinline__ T angle_error_small(T d) {   // d = psi_d - psi, |d| < 2 pi
+    const T tp = T(MVRL_TWO_PI);
+    const T a = pymod_small(d, tp), b = pymod_small(-d, tp);
+    return a < b ? a : -b;
+}
 template <typename T> __device__ __forceinline__ T angle_error(T psi_d, T psi) {
     const T tp = T(MVRL_TWO_PI);
-    T a = pymod_pos(psi_d - psi, tp);
-    T b = pymod_pos(psi - psi_d, tp);
+    const T d = psi_d - psi;                 // psi - psi_d == -d exactly
+    if (tabs(d) < tp) return angle_error_small(d);
+    const T a = pymod_general(d, tp), b = pymod_general(-d, tp);
     return a < b ? a : -b;
 }
 
 #ifndef MVRL_POSE_COMP
 #define MVRL_POSE_COMP 1
 #endif
+#ifndef MVRL_TRIG_ANCHOR
+#define MVRL_TRIG_ANCHOR 1
+#endif
+__device__ __forceinline__ F2 angle_error(F2 psi_d, F2 psi) {
+    return F2(angle_error(psi_d.v.x, psi.v.x), angle_error(psi_d.v.y, psi.v.y));
+}
+
 // y += inc with a Kahan carry (compensated summation across RK4 sub-steps)
 template <typename T> __device__ __forceinline__ void rk4_pose_update(T& y, T& carry, T inc) {
     const T t = inc - carry;

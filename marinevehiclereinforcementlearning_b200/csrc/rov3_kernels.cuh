@@ -156,6 +156,9 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
     } else {
         sp[2] = a.setpoint[2 * ld + i];
     }
+    T path[4];   // epilogue input, loaded early so the latency hides behind the RK4 loop
+#pragma unroll
+    for (int k = 0; k < 4; ++k) path[k] = a.path[k * ld + i];
     T gcf[3] = {T(0), T(0), T(0)};
     T rpm[4];
     if constexpr (MODE == ACT_RPM) {
@@ -201,9 +204,6 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < 6; ++k) bad = bad || !finite_t(y[k]);
-    T path[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) path[k] = a.path[k * ld + i];
     T obs[5];
     observe3(P, y, path, sp[2], obs);
     const bool is_done = istep >= a.max_steps;
@@ -213,7 +213,7 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) a.aux[(3 + k) * ld + i] = rpm[k];
     }
-    if (a.stats != nullptr) stats_accumulate(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
+    if (a.stats != nullptr) stats_accumulate<false>(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
     int istep_out = istep;
     if (is_done && a.auto_reset) {
         if (a.term_obs != nullptr) {

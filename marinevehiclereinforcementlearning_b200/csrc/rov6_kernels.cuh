@@ -31,22 +31,61 @@ __device__ __forceinline__ void observe6(const Rov6Dev<T>& P, const T (&y)[12], 
     }
 }
 
+// 6DoF.py:560 + 467-483 on the fast path: wraps the three angles and fills the observation assuming every
+// angle and every angle error is inside (-2 pi, 2 pi); returns false when that does not hold (the caller
+// then redoes the angle part with the exact, out-of-line functions).  One compare at the end instead
+// of a branch per modulo.
+template <typename T>
+__device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T (&y)[12], const T (&path)[6], const T (&sp_ang)[3],
+                                                   T (&wrapped)[3], T (&obs)[9]) {
+    const T tp = T(MVRL_TWO_PI);
+    T worst = T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        worst = tmax(worst, tabs(y[3 + k]));
+        wrapped[k] = pymod_small(y[3 + k], tp);
+        const T d = sp_ang[k] - wrapped[k];
+        worst = tmax(worst, tabs(d));
+        obs[k] = clampt((path[k] - y[k]) * P.inv_3L, T(-1), T(1));
+        obs[3 + k] = clampt((path[3 + k] - y[k]) * P.inv_3L, T(-1), T(1));
+        obs[6 + k] = clampt(angle_error_small(d) * P.inv_ang, T(-1), T(1));
+    }
+    return worst < tp;
+}
+
+// the exact angle part (any magnitude), out of line: wrapped angle and clipped, scaled angle error
+template <typename T> struct WrapObs { T wrapped, obs; };   // returned by value: stays in registers
+template <typename T>
+__device__ __noinline__ WrapObs<T> wrap_angle_exact(T inv_ang, T angle, T sp_angle) {
+    WrapObs<T> r;
+    r.wrapped = pymod_pos(angle, T(MVRL_TWO_PI));
+    r.obs = clampt(angle_error(sp_angle, r.wrapped) * inv_ang, T(-1), T(1));
+    return r;
+}
+
 // Random branch of reset().  The reference's own line raises (6DoF.py:497,
 // shapes (2,3)-(2,)); defined here as the 3-component analogue of 3DoF.py:423:
-// path = (U^(2x3) - 0.5) * 10, targetOrientation = U^3 * 2 pi.
+// path = (U^(2x3) - 0.5) * 10, targetOrientation = U^3 * 2 pi.  Out of line: taken by one
+// environment in max_steps, and three Philox blocks would bloat the common path.
+template <typename T> struct Reset6 { T path[6]; T orient[3]; };
 template <typename T>
-__device__ __forceinline__ void draw_reset6(unsigned long long seed, unsigned long long env, uint32_t episode, T (&path)[6], T (&orient)[3]) {
+__device__ __noinline__ Reset6<T> draw_reset6(unsigned long long seed, unsigned long long env, uint32_t episode) {
     const uint4 a = Philox::draw(seed, env, episode, 0u, 0u);
     const uint4 b = Philox::draw(seed, env, episode, 0u, 1u);
     const uint4 c = Philox::draw(seed, env, episode, 0u, 2u);
-    path[0] = (u01<T>(a.x) - T(0.5)) * T(10); path[1] = (u01<T>(a.y) - T(0.5)) * T(10);
-    path[2] = (u01<T>(a.z) - T(0.5)) * T(10); path[3] = (u01<T>(a.w) - T(0.5)) * T(10);
-    path[4] = (u01<T>(b.x) - T(0.5)) * T(10); path[5] = (u01<T>(b.y) - T(0.5)) * T(10);
-    orient[0] = u01<T>(b.z) * T(MVRL_TWO_PI); orient[1] = u01<T>(b.w) * T(MVRL_TWO_PI);
-    orient[2] = u01<T>(c.x) * T(MVRL_TWO_PI);
+    Reset6<T> r;
+    r.path[0] = (u01<T>(a.x) - T(0.5)) * T(10); r.path[1] = (u01<T>(a.y) - T(0.5)) * T(10);
+    r.path[2] = (u01<T>(a.z) - T(0.5)) * T(10); r.path[3] = (u01<T>(a.w) - T(0.5)) * T(10);
+    r.path[4] = (u01<T>(b.x) - T(0.5)) * T(10); r.path[5] = (u01<T>(b.y) - T(0.5)) * T(10);
+    r.orient[0] = u01<T>(b.z) * T(MVRL_TWO_PI); r.orient[1] = u01<T>(b.w) * T(MVRL_TWO_PI);
+    r.orient[2] = u01<T>(c.x) * T(MVRL_TWO_PI);
+    return r;
 }
 
 // episode statistics: [episodes, sum length, sum return, min return, max return, non-finite, -, -]
+// WITH_RET = false: the env's reward is identically zero (3DoF / 6DoF), so the return statistics are
+// the constants 0 - written by plain stores (every writer stores the same value) instead of CAS loops.
+template <bool WITH_RET = true>
 __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, double len, double ret, bool bad) {
     const unsigned active = __activemask();
     const unsigned dm = __ballot_sync(active, is_done);
@@ -56,15 +95,22 @@ __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, do
     const int leader = __ffs(active) - 1;
     if (dm) {
         const double sl = warp_sum(is_done ? len : 0.0, active);
-        const double sr = warp_sum(is_done ? ret : 0.0, active);
-        const double mn = warp_min(is_done ? ret : 1.0e300, active);
-        const double mx = warp_max(is_done ? ret : -1.0e300, active);
-        if (lane == leader) {
+        if constexpr (WITH_RET) {
+            const double sr = warp_sum(is_done ? ret : 0.0, active);
+            const double mn = warp_min(is_done ? ret : 1.0e300, active);
+            const double mx = warp_max(is_done ? ret : -1.0e300, active);
+            if (lane == leader) {
+                atomicAdd(stats + 0, (double)__popc(dm));
+                atomicAdd(stats + 1, sl);
+                atomicAdd(stats + 2, sr);
+                atomic_min_double(stats + 3, mn);
+                atomic_max_double(stats + 4, mx);
+            }
+        } else if (lane == leader) {
             atomicAdd(stats + 0, (double)__popc(dm));
             atomicAdd(stats + 1, sl);
-            atomicAdd(stats + 2, sr);
-            atomic_min_double(stats + 3, mn);
-            atomic_max_double(stats + 4, mx);
+            stats[3] = 0.0;
+            stats[4] = 0.0;
         }
     }
     if (bm && lane == leader) atomicAdd(stats + 5, (double)__popc(bm));
@@ -73,6 +119,9 @@ __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, do
 // ---------------------------------------------------------------------------
 // K1: fused env step.  action -> (set-point) -> n_sub x RK4 in registers ->
 // wrap -> observation -> done -> reward -> auto-reset.
+// V = float / double: one environment per thread.  V = F2: two fp32 environments
+// per thread (2t, 2t + 1) on the packed FFMA2 path; loads / stores are 8-byte
+// vectors, the (cheap, branchy) epilogue runs per lane.
 // ---------------------------------------------------------------------------
 #ifndef MVRL_STEP_BLOCK
 #define MVRL_STEP_BLOCK 128
@@ -80,77 +129,104 @@ __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, do
 #ifndef MVRL_STEP_MINB
 #define MVRL_STEP_MINB 1
 #endif
+// launch shape of the two-environments-per-thread (F2) instantiation
+#ifndef MVRL_STEP_BLOCK_X2
+#define MVRL_STEP_BLOCK_X2 128
+#endif
+#ifndef MVRL_STEP_MINB_X2
+#define MVRL_STEP_MINB_X2 3   // <= 168 registers: 3 CTAs = 12 warps per SM (measured best, profiles/ r1e notes)
+#endif
+template <typename V> struct StepLaunch { static constexpr int BLOCK = MVRL_STEP_BLOCK, MINB = (sizeof(V) == 4 ? MVRL_STEP_MINB : 1); };
+template <> struct StepLaunch<F2> { static constexpr int BLOCK = MVRL_STEP_BLOCK_X2, MINB = MVRL_STEP_MINB_X2; };
 
-template <typename T, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
-__global__ void __launch_bounds__(MVRL_STEP_BLOCK, (sizeof(T) == 4 ? MVRL_STEP_MINB : 1))
-rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+// SoA element access for one thread: environments i0 .. i0 + L - 1 of row p
+template <typename V, typename S> __device__ __forceinline__ V load_v(const S* p, long i0, bool pair) {
+    if constexpr (VT<V>::L == 1) { (void)pair; return p[i0]; }
+    else { if (pair) return f2_from(*reinterpret_cast<const float2*>(p + i0)); return F2(p[i0], 0.0f); }
+}
+template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, long i0, bool pair, V x) {
+    if constexpr (VT<V>::L == 1) { (void)pair; p[i0] = x; }
+    else { if (pair) *reinterpret_cast<float2*>(p + i0) = x.v; else p[i0] = x.v.x; }
+}
+
+template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
+__global__ void __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
+rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
+    using T = typename VT<V>::S;
+    constexpr int L = VT<V>::L;
+    const long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * L;
+    if (i0 >= a.n) return;
+    const bool pair = (L == 2) && (i0 + 1 < a.n);   // second lane holds a real environment
     const Rov6Dev<T>& P = a.P;
     const long ld = a.ld;
     constexpr bool EXACT = (sizeof(T) == 8);
 
-    T y[12];
+    V y[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) y[k] = a.state[k * ld + i];
-    const int istep = a.istep[i] + 1;
+    for (int k = 0; k < 12; ++k) y[k] = load_v<V>(a.state + k * ld, i0, pair);
 
     constexpr int NA = (MODE == ACT_RPM) ? 8 : 6;
-    T act[NA];
+    V act[NA];
 #pragma unroll
-    for (int k = 0; k < NA; ++k) act[k] = a.action[k * ld + i];
+    for (int k = 0; k < NA; ++k) act[k] = load_v<V>(a.action + k * ld, i0, pair);
+    // needed by the epilogue only, but issued here so that their DRAM latency hides behind the RK4 loop
+    V path_v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) path_v[k] = load_v<V>(a.path + k * ld, i0, pair);
+    int istep_in[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) istep_in[l] = (l == 0 || pair) ? a.istep[i0 + l] : 0;
 
-    T sp[6];
-    T e_old[6], e_int[6];
+    V sp[6];
+    V e_old[6], e_int[6];
     if constexpr (MODE == ACT_SETPOINT) {
         if (a.fixed_sp) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) sp[k] = a.setpoint[k * ld + i];
+            for (int k = 0; k < 6; ++k) sp[k] = load_v<V>(a.setpoint + k * ld, i0, pair);
         } else {  // 6DoF.py:545-552
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                sp[k] = act[k] * P.act_pos + y[k];
-                sp[3 + k] = act[3 + k] * P.act_ang + y[3 + k];
+                sp[k] = act[k] * V(P.act_pos) + y[k];
+                sp[3 + k] = act[3 + k] * V(P.act_ang) + y[3 + k];
             }
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { e_old[k] = a.ctrl[k * ld + i]; e_int[k] = a.ctrl[(6 + k) * ld + i]; }
+        for (int k = 0; k < 6; ++k) { e_old[k] = load_v<V>(a.ctrl + k * ld, i0, pair); e_int[k] = load_v<V>(a.ctrl + (6 + k) * ld, i0, pair); }
     } else {
 #pragma unroll
-        for (int k = 3; k < 6; ++k) sp[k] = a.setpoint[k * ld + i];
+        for (int k = 3; k < 6; ++k) sp[k] = load_v<V>(a.setpoint + k * ld, i0, pair);
     }
 
-    T H[6];       // thruster wrench of the current evaluation
-    T gcf[6];     // generalisedControlForces of the last evaluation
-    T dem[8];     // allocated demand (N) of the last evaluation
+    V H[6];       // thruster wrench of the current evaluation
+    V gcf[6];     // generalisedControlForces of the last evaluation
+    V dem[8];     // allocated demand (N) of the last evaluation
     if constexpr (MODE == ACT_RPM) {
-        T F[8];
+        V F[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) F[k] = thruster_force(P, act[k]);
-        thrust_wrench<T, SP>(P, F, H);  // rpm is held over the env step: hoisted out of RK4
+        thrust_wrench<V, SP>(P, F, H);  // rpm is held over the env step: hoisted out of RK4
     } else if constexpr (MODE == ACT_FORCE) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) gcf[k] = act[k];
     }
 
     // one derivative evaluation; dtc = t - tOld of the PID (0 or h/2 inside a step)
-    auto f = [&](const T (&s)[12], T (&k)[12], T dtc) {
-        const Trig6<T> g = trig6<T, FAST>(s[3], s[4], s[5]);
-        const T nu[6] = {s[6], s[7], s[8], s[9], s[10], s[11]};
+    auto f = [&](const Trig6<V>& g, const V (&s)[12], V (&k)[12], T dtc) {
+        const V nu[6] = {s[6], s[7], s[8], s[9], s[10], s[11]};
         if constexpr (MODE != ACT_RPM) {
             if constexpr (MODE == ACT_SETPOINT) {
-                const T pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
+                const V pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
                 pid6(P, e_old, e_int, sp, pose, dtc, gcf);
             }
-            allocate_demand<T, SP>(P, g, gcf, dem);
-            T F[8];
+            allocate_demand<V, SP>(P, g, gcf, dem);
+            V F[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) F[j] = demand_to_force<T, EXACT>(P, dem[j]);
-            thrust_wrench<T, SP>(P, F, H);
+            for (int j = 0; j < 8; ++j) F[j] = demand_to_force<V, EXACT>(P, dem[j]);
+            thrust_wrench<V, SP>(P, F, H);
         }
-        T ed[6], acc[6], rhs[6];
-        kinematics6<T, FAST>(g, nu, ed);
-        body_accel<T, SP>(P, g, nu, H, acc, rhs);
+        V ed[6], acc[6], rhs[6];
+        kinematics6<V, FAST>(g, nu, ed);
+        body_accel<V, SP>(P, g, nu, H, acc, rhs);
 #pragma unroll
         for (int j = 0; j < 6; ++j) { k[j] = ed[j]; k[6 + j] = acc[j]; }
     };
@@ -160,24 +236,49 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
     // pose (pure integrators: every rounding error stays) is advanced in fp32 by the separately
     // summed increment with a Kahan carry across the sub-steps, i.e. about one rounding at ulp(y)
     // per env step instead of 4 n_sub (rk4_pose_update; keeps 1000-step fp32 trajectories within 1e-4).
+    // fp32 trigonometry: full sin/cos once per sub-step (stage 1); stages 2-4 sit at angle + c_k k,
+    // a small known offset, and use the addition theorem (sincos_delta) unless the offset is large.
     constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
+    constexpr bool ANCHOR = (sizeof(T) == 4) && !FAST && (MVRL_TRIG_ANCHOR != 0);
     const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6), h3 = a.h / T(3);
-    T carry[6];
+    V carry[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) carry[j] = T(0);
+    for (int j = 0; j < 6; ++j) carry[j] = V(T(0));
     for (int sub = 0; sub < a.n_sub; ++sub) {
-        T k[12], acc[12], yt[12];
+        V k[12], acc[12], yt[12];
+        Trig6<V> g0;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) { acc[j] = (COMP && j < 6) ? T(0) : y[j]; yt[j] = y[j]; }
+        for (int j = 0; j < 12; ++j) { acc[j] = (COMP && j < 6) ? V(T(0)) : y[j]; yt[j] = y[j]; }
 #pragma unroll STAGE_UNROLL
         for (int st = 0; st < 4; ++st) {
-            f(yt, k, (st & 1) ? hh : T(0));
+            Trig6<V> g;
+            if constexpr (ANCHOR) {
+                if (st == 0) {
+                    g0 = trig6<V, FAST>(y[3], y[4], y[5]);
+                    g = g0;
+                } else {
+                    const T cp = (st == 3) ? h : hh;          // this stage's state is y + cp * k(previous stage)
+                    const V d0 = V(cp) * k[3], d1 = V(cp) * k[4], d2 = V(cp) * k[5];
+                    const V z0 = d0 * d0, z1 = d1 * d1, z2 = d2 * d2;
+                    const V zs = z0 + z1 + z2;
+                    if (!vany(vgt(zs, V(MVRL_TRIG_DELTA_MAX2)))) {   // (NaN offsets take the cheap path and stay NaN)
+                        sincos_delta(g0.sph, g0.cph, d0, z0, &g.sph, &g.cph);
+                        sincos_delta(g0.sth, g0.cth, d1, z1, &g.sth, &g.cth);
+                        sincos_delta(g0.sps, g0.cps, d2, z2, &g.sps, &g.cps);
+                    } else {
+                        g = trig6<V, FAST>(yt[3], yt[4], yt[5]);
+                    }
+                }
+            } else {
+                g = trig6<V, FAST>(yt[3], yt[4], yt[5]);
+            }
+            f(g, yt, k, (st & 1) ? hh : T(0));
             const T wk = (st == 0 || st == 3) ? h6 : h3;
             const T ck = (st == 2) ? h : hh;
 #pragma unroll
             for (int j = 0; j < 12; ++j) {
-                acc[j] = fmaf_t(wk, k[j], acc[j]);
-                if (st < 3) yt[j] = fmaf_t(ck, k[j], y[j]);
+                acc[j] = fmaf_t(V(wk), k[j], acc[j]);
+                if (st < 3) yt[j] = fmaf_t(V(ck), k[j], y[j]);
             }
         }
 #pragma unroll
@@ -187,85 +288,126 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<T> a) {
         }
     }
 
-    bool bad = false;
-    if constexpr (sizeof(T) == 4 && !FAST) {  // outside the exact range of the fp32 sin/cos reduction
+    // ---- epilogue, per environment (scalar): wrap, observe, done, stats, auto-reset ----
+    V nonfinite = V(T(0));   // sum of 0 * y_k: 0 when every state is finite, NaN otherwise
 #pragma unroll
-        for (int k = 3; k < 6; ++k) bad = bad || tabs(y[k]) > T(MVRL_SINCOS_F32_MAX_ARG);
+    for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
+    V obs_v[9], sp_v[6], eo_v[6], ei_v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sp_v[k] = sp[k]; eo_v[k] = e_old[k]; ei_v[k] = e_int[k]; }
+    if constexpr (MODE != ACT_SETPOINT) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sp_v[k] = V(T(0));
     }
-    // 6DoF.py:560
 #pragma unroll
-    for (int k = 3; k < 6; ++k) y[k] = pymod_pos(y[k], T(MVRL_TWO_PI));
+    for (int l = 0; l < L; ++l) {
+        if (l == 1 && !pair) break;
+        const long i = i0 + l;
+        T ys[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) bad = bad || !finite_t(y[k]);
+        for (int k = 0; k < 12; ++k) ys[k] = lane_get(y[k], l);
+        const int istep = istep_in[l] + 1;
+        bool bad = lane_get(nonfinite, l) != T(0);   // NaN compares unequal
+        if constexpr (sizeof(T) == 4 && !FAST) {  // outside the exact range of the fp32 sin/cos reduction
+            bad = bad || tmax(tmax(tabs(ys[3]), tabs(ys[4])), tabs(ys[5])) > T(MVRL_SINCOS_F32_MAX_ARG);
+        }
+        T path[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
+        T sps[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sps[k] = lane_get(sp_v[k], l);
+        const T spa[3] = {sps[3], sps[4], sps[5]};
+        T obs[9], wrapped[3];
+        // 6DoF.py:560 (wrap) and 467-483 (dataToState)
+        if (!wrap_observe6_fast(P, ys, path, spa, wrapped, obs)) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const WrapObs<T> r = wrap_angle_exact(P.inv_ang, ys[3 + k], spa[k]);
+                wrapped[k] = r.wrapped; obs[6 + k] = r.obs;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ys[3 + k] = wrapped[k];
+        const bool is_done = istep >= a.max_steps;  // 6DoF.py:569-571
 
-    T path[6];
+        if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
+            if constexpr (MODE == ACT_RPM) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) path[k] = a.path[k * ld + i];
-    const T spa[3] = {sp[3], sp[4], sp[5]};
-    T obs[9];
-    observe6(P, y, path, spa, obs);
-    const bool is_done = istep >= a.max_steps;  // 6DoF.py:569-571
+                for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = T(0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = lane_get(act[k], l);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = lane_get(gcf[k], l);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, T(lane_get(dem[k], l)));
+            }
+        }
+        if (a.stats != nullptr) stats_accumulate<false>(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
 
-    if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
-        if constexpr (MODE == ACT_RPM) {
+        int istep_out = istep;
+        T eo[6], ei[6];
+        if constexpr (MODE == ACT_SETPOINT) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = T(0);
+            for (int k = 0; k < 6; ++k) { eo[k] = lane_get(eo_v[k], l); ei[k] = lane_get(ei_v[k], l); }
+        }
+        if (is_done && a.auto_reset) {
+            if (a.term_obs != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = act[k];
-        } else {
+                for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = obs[k];
+            }
+            const uint32_t ep = a.episode[i] + 1u;
+            a.episode[i] = ep;
+            istep_out = 0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = gcf[k];
+            for (int k = 0; k < 12; ++k) ys[k] = T(0);
+            if (!a.fixed_sp) {
+                const Reset6<T> rs = draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, dem[k]);
+                for (int k = 0; k < 6; ++k) { path[k] = rs.path[k]; a.path[k * ld + i] = path[k]; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sps[k] = path[k]; sps[3 + k] = rs.orient[k]; }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a.setpoint[k * ld + i] = sps[k];
+            }
+            if constexpr (MODE == ACT_SETPOINT) {  // fresh controller, 6DoF.py:37-41, 514
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { eo[k] = T(0); ei[k] = T(0); }
+                eo[0] = Real<T>::nan();
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                obs[k] = clampt(path[k] * P.inv_3L, T(-1), T(1));        // the fresh state is zero
+                obs[3 + k] = clampt(path[3 + k] * P.inv_3L, T(-1), T(1));
+                obs[6 + k] = wrap_angle_exact(P.inv_ang, T(0), sps[3 + k]).obs;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) lane_set(y[k], l, ys[k]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) lane_set(obs_v[k], l, obs[k]);
+        a.done[i] = is_done ? 1 : 0;
+        a.istep[i] = istep_out;
+        if constexpr (MODE == ACT_SETPOINT) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { lane_set(sp_v[k], l, sps[k]); lane_set(eo_v[k], l, eo[k]); lane_set(ei_v[k], l, ei[k]); }
+            a.ctrl[12 * ld + i] = T(istep_out) * a.dt;
         }
     }
-    if (a.stats != nullptr) stats_accumulate(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
-
-    int istep_out = istep;
-    if (is_done && a.auto_reset) {
-        if (a.term_obs != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = obs[k];
-        }
-        const uint32_t ep = a.episode[i] + 1u;
-        a.episode[i] = ep;
-        istep_out = 0;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) y[k] = T(0);
-        if (!a.fixed_sp) {
-            T orient[3];
-            draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep, path, orient);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) a.path[k * ld + i] = path[k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { sp[k] = path[k]; sp[3 + k] = orient[k]; }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) a.setpoint[k * ld + i] = sp[k];
-        }
-        if constexpr (MODE == ACT_SETPOINT) {  // fresh controller, 6DoF.py:37-41, 514
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { e_old[k] = T(0); e_int[k] = T(0); }
-            e_old[0] = Real<T>::nan();
-        }
-        const T spa2[3] = {sp[3], sp[4], sp[5]};
-        observe6(P, y, path, spa2, obs);
-    }
 
 #pragma unroll
-    for (int k = 0; k < 12; ++k) a.state[k * ld + i] = y[k];
+    for (int k = 0; k < 12; ++k) store_v<V>(a.state + k * ld, i0, pair, y[k]);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) a.obs[k * ld + i] = obs[k];
-    a.reward[i] = T(0);  // 6DoF.py:575
-    a.done[i] = is_done ? 1 : 0;
-    a.istep[i] = istep_out;
+    for (int k = 0; k < 9; ++k) store_v<V>(a.obs + k * ld, i0, pair, obs_v[k]);
+    store_v<V>(a.reward, i0, pair, V(T(0)));  // 6DoF.py:575
     if constexpr (MODE == ACT_SETPOINT) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            a.setpoint[k * ld + i] = sp[k];
-            a.ctrl[k * ld + i] = e_old[k];
-            a.ctrl[(6 + k) * ld + i] = e_int[k];
+            store_v<V>(a.setpoint + k * ld, i0, pair, sp_v[k]);
+            store_v<V>(a.ctrl + k * ld, i0, pair, eo_v[k]);
+            store_v<V>(a.ctrl + (6 + k) * ld, i0, pair, ei_v[k]);
         }
-        a.ctrl[12 * ld + i] = T(istep_out) * a.dt;
     }
 }
 
@@ -365,11 +507,12 @@ rov6_reset_kernel(const __grid_constant__ Rov6ResetArgs<T> a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) { path[k] = sp[k]; path[3 + k] = sp[k]; }
     } else {
-        T orient[3];
         const uint32_t ep = a.episode ? a.episode[i] : 0u;
-        draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep, path, orient);
+        const Reset6<T> rs = draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { sp[k] = path[k]; sp[3 + k] = orient[k]; }
+        for (int k = 0; k < 6; ++k) path[k] = rs.path[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sp[k] = path[k]; sp[3 + k] = rs.orient[k]; }
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) { a.path[k * ld + i] = path[k]; a.setpoint[k * ld + i] = sp[k]; }
