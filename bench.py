@@ -120,10 +120,19 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_port_rate(n_envs, n_steps, threads=0, seed=1234):
     """env-steps/s of the C port of the reference's step loop on the host."""
     from oracle import c_oracle as c
     from oracle import oracle_np as o
+    threads = threads or host_threads()
     env = c.Rov6EnvC(n_envs, mode=o.MODE_RPM, max_steps=MAX_STEPS, n_sub=N_SUB, dt=DT, auto_reset=True, seed=seed, threads=threads)
     env.reset()
     rng = np.random.default_rng(seed)
@@ -133,8 +142,7 @@ def cpu_port_rate(n_envs, n_steps, threads=0, seed=1234):
     for k in range(n_steps):
         env.step(acts[k % 4])
     dt = time.perf_counter() - t0
-    used = threads if threads > 0 else c.load().orc_max_threads()
-    return n_envs * n_steps / dt, dt, used
+    return n_envs * n_steps / dt, dt, threads
 
 
 def python_port_rate(seconds=3.0):
@@ -157,8 +165,8 @@ def run_reference(args, rank, world):
     n_envs = 32768
     from oracle import c_oracle as c
     from oracle import oracle_np as o
-    threads = c.load().orc_max_threads()
-    env = c.Rov6EnvC(n_envs, mode=o.MODE_RPM, max_steps=MAX_STEPS, n_sub=N_SUB, dt=DT, auto_reset=True, seed=1234)
+    threads = host_threads()
+    env = c.Rov6EnvC(n_envs, mode=o.MODE_RPM, max_steps=MAX_STEPS, n_sub=N_SUB, dt=DT, auto_reset=True, seed=1234, threads=threads)
     env.reset()
     rng = np.random.default_rng(1234)
     acts = rng.uniform(-3500.0, 3500.0, (4, n_envs, 8))
