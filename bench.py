@@ -333,6 +333,180 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------
+# secondary workloads (BASELINE configs 4 and 5); same JSON shape, selected with --workload
+def _timed(dev, world, fn, steps, warmup):
+    """W untimed + K timed calls of fn(k) between barriers; returns (ms total max over ranks, clocks)."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for k in range(warmup):
+        fn(k)
+    barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for k in range(steps):
+        fn(k)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), sampler.stop(t0, t1)
+
+
+def run_auv(args, rank, local_rank, world):
+    """Config 4: legacy AuvEnv, 262 144 envs per GPU, fp32, synthetic turbulence field [2000, 41, 61] scaled like
+    verySimpleAuv.py:104, a ~ U(-1, 1)^3, noiseMag* = 0.1.  One step = one auv_step launch over the batch."""
+    import torch
+    import torch.distributed as dist
+    from marinevehiclereinforcementlearning_b200 import AuvVecEnv
+    from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence import flowGenerator
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs if args.envs != ENVS_PER_GPU else 262144
+    ltm = np.load(os.path.join(ROOT, "tests", "golden", "golden_legacy.npz"))["ltm"]   # the reference's ltm.npy (41 x 61 x 3)
+    flow = flowGenerator.ReconstructedFlow.synthetic(lt_mean=ltm, nt=2000, seed=7, sigma=0.05, kind=args.field, dtype=torch.float32, device=dev)
+    flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    env = AuvVecEnv(n, flow, seed=1234, env_id0=rank * n, noiseMagCoeffs=0.1, noiseMagActuation=0.1, auto_reset=True,
+                    dtype=torch.float32, record_terminal_obs=False)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = [torch.rand((3, env.ld), generator=gen, device=dev) * 2 - 1 for _ in range(8)]
+
+    def one_step(k):
+        env._bufs.action = acts[k % 8].data_ptr()
+        env.step_async()
+    graph = None
+    for k in range(3):
+        one_step(k)
+    if args.graph:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for k in range(args.steps):
+                    one_step(k)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ms, clocks = _timed(dev, world, lambda k: graph.replay() if k == 0 else None, 1, 0)
+        ms, clocks = _timed(dev, world, lambda k: graph.replay(), 1, 1)
+    else:
+        ms, clocks = _timed(dev, world, one_step, args.steps, args.warmup)
+    stats = env.episode_stats()
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        rate = n / (ms / args.steps * 1e-3)
+        # state 6 r/w, action 3 r, obs 11 w, reward w, mults 11 r, target 2 r, err_o 3 r/w, ring 30 r + 3 w, return r/w, done 1, istep 8
+        nbytes = (12 + 3 + 11 + 1 + 11 + 2 + 6 + 33 + 2) * 4 + 9
+        line = {"metric": "legacy AuvEnv env-steps/sec", "value": world * rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "auv_step fp32: legacy verySimpleAuv, %d envs/GPU, field [2000,41,61,2] (%s), a~U(-1,1)^3" % (n, args.field),
+                           "cuda_graph": bool(args.graph), "smem_staged_gather": os.environ.get("MVRL_AUV_NO_STAGE", "0") != "1",
+                           "l2": "40 MB field is L2-resident by design; per-env arrays (87 MB / step) rotate through 8 action batches"},
+                "roofline": {"bound": "hbm", "achieved": rate * nbytes / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": rate * nbytes / 1e9 / peaks["hbm_gbs"], "traffic": None, "bytes_per_env_step": nbytes,
+                             "gathered_bytes_per_env_step_from_l2": 64, "peak_source": peak_src},
+                "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rollout(args, rank, local_rank, world):
+    """Config 5: rollout collection over the 6DoF env in the reference's Gym semantics (PID set-point actions):
+    131 072 envs per GPU, policy MLP 9-128-128-128-6 (GELU, arch of legacy/main_00_sbl.py:100-105) + Gaussian head in
+    PyTorch on the feature-major observation buffer, 128-step rollouts replayed as one CUDA graph, episode statistics
+    all-reduced once per rollout.  Reported: env-steps/s including the policy."""
+    import torch
+    import torch.distributed as dist
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = args.envs if args.envs != ENVS_PER_GPU else 131072
+    T = args.rollout_len
+    env = BlueROV2Heavy6DoFVecEnv(n, action_mode="setpoint", dtype=torch.float32, device=dev, n_sub=args.n_sub, seed=1234,
+                                  env_id0=rank * n, auto_reset=True, record_terminal_obs=False)
+    env.reset()
+    torch.manual_seed(1234 + rank)
+    dims = [9, 128, 128, 128, 6]
+    Ws = [torch.randn(dims[i + 1], dims[i], device=dev) / dims[i] ** 0.5 for i in range(4)]
+    bs = [torch.zeros(dims[i + 1], 1, device=dev) for i in range(4)]
+    log_std = torch.full((6, 1), -0.5, device=dev)
+    ld = env.ld
+    buf_obs = torch.empty((T, 9, ld), device=dev)
+    buf_act = torch.empty((T, 6, ld), device=dev)
+    buf_logp = torch.empty((T, ld), device=dev)
+    buf_rew = torch.empty((T, ld), device=dev)
+    buf_done = torch.empty((T, ld), dtype=torch.uint8, device=dev)
+
+    def policy(x):            # feature-major: x [9, N] -> mean [6, N]; W x needs no transposes of the SoA buffers
+        for i in range(3):
+            x = torch.nn.functional.gelu(torch.addmm(bs[i], Ws[i], x))
+        return torch.tanh(torch.addmm(bs[3], Ws[3], x))
+
+    def rollout():
+        for t in range(T):
+            obs = env._obs
+            buf_obs[t].copy_(obs)
+            mean = policy(obs)
+            eps = torch.randn_like(mean)
+            act = (mean + eps * log_std.exp()).clamp_(-1., 1.)
+            buf_logp[t].copy_((-0.5 * eps * eps - log_std).sum(0))
+            buf_act[t].copy_(act)
+            env._bufs.action = buf_act[t].data_ptr()
+            env.step_async()
+            buf_rew[t].copy_(env._reward)
+            buf_done[t].copy_(env._done)
+    rollout()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            rollout()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    stats_holder = {}
+
+    def one_rollout(k):
+        graph.replay()
+        stats_holder["s"] = env.episode_stats()     # K5: device accumulators -> all-reduce (NCCL) -> host, once per rollout
+    rollouts = max(2, args.steps // T)
+    ms, clocks = _timed(dev, world, one_rollout, rollouts, max(1, args.warmup // T))
+    if rank == 0:
+        rate = n * T * rollouts / (ms * 1e-3)
+        flop_env = flop_per_env_step("setpoint", args.n_sub)
+        flop_policy = 2 * sum(dims[i] * dims[i + 1] for i in range(4))
+        line = {"metric": "6DoF rollout collection env-steps/sec (policy included)", "value": world * rate, "unit": UNIT, "n_gpus": world,
+                "steps": rollouts * T, "warmup": max(1, args.warmup // T) * T, "ms_per_step": ms / (rollouts * T), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy matmuls TF32)", "data": "synthetic",
+                "config": {"workload": "rollout: 6DoF set-point env + MLP 9-128-128-128-6 GELU Gaussian policy, %d envs/GPU, %d-step rollouts, "
+                                       "nSub=%d, CUDA-graph replay, stats all-reduce per rollout" % (n, T, args.n_sub)},
+                "flop_per_env_step": {"env": flop_env, "policy": flop_policy},
+                "gpu_launches": rollouts * T, "clocks": clocks, "episode_stats": stats_holder.get("s")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,6 +521,10 @@ def main():
     ap.add_argument("--action-mode", default="rpm", choices=["rpm", "force", "setpoint"], help="default rpm = BASELINE config 3")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--n-sub", type=int, default=N_SUB)
+    ap.add_argument("--workload", default="rov6", choices=["rov6", "auv", "rollout"],
+                    help="rov6 = BASELINE config 3 (the metric); auv = config 4; rollout = config 5")
+    ap.add_argument("--field", default="modes", choices=["modes", "noise"], help="auv: synthetic turbulence stand-in")
+    ap.add_argument("--rollout-len", type=int, default=128)
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
     ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
     ap.add_argument("--no-stats", action="store_true", help="diagnostics: do not accumulate episode statistics in the step kernel")
@@ -358,6 +536,10 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "auv":
+        run_auv(args, rank, local_rank, world)
+    elif args.workload == "rollout":
+        run_rollout(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -17,30 +17,74 @@ template <typename T> struct FlowDev {
 
 // flowGenerator.py:97-136: trilinear interpolation, indices clamped to the grid,
 // weights NOT clamped (extrapolation outside, and `translate` is ignored).
+template <typename T> struct FlowCell { int kk, jj, ii; T wt, wx, wy; };
+
+template <typename T>
+__device__ __forceinline__ FlowCell<T> flow_locate(const FlowDev<T>& f, T time, T x, T y) {
+    const T tt = time / f.dt, xx = x / f.dx, yy = y / f.dy;
+    FlowCell<T> c;
+    // clamp in floating point first: int conversion of huge / non-finite values is undefined
+    c.kk = (int)tmin(T(f.nt - 2), tmax(T(0), Real<T>::floor(tt)));
+    c.ii = (int)tmin(T(f.nx - 2), tmax(T(0), Real<T>::floor(xx)));
+    c.jj = (int)tmin(T(f.ny - 2), tmax(T(0), Real<T>::floor(yy)));
+    c.wt = tt - T(c.kk); c.wx = xx - T(c.ii); c.wy = yy - T(c.jj);
+    return c;
+}
+
+// weights applied in the reference's order: along x, then y, then time
+template <typename T>
+__device__ __forceinline__ T flow_blend(const FlowCell<T>& c, T c000, T c001, T c010, T c011, T c100, T c101, T c110, T c111) {
+    const T r00 = c000 * (T(1) - c.wx) + c001 * c.wx, r01 = c010 * (T(1) - c.wx) + c011 * c.wx;
+    const T r10 = c100 * (T(1) - c.wx) + c101 * c.wx, r11 = c110 * (T(1) - c.wx) + c111 * c.wx;
+    return ((T(1) - c.wy) * r00 + c.wy * r01) * (T(1) - c.wt) + ((T(1) - c.wy) * r10 + c.wy * r11) * c.wt;
+}
+
 // Gathers 8 corners x NOUT components straight from L2 (read-only path).
 template <typename T, int NOUT>
 __device__ __forceinline__ void flow_interp(const FlowDev<T>& f, T time, T x, T y, T (&res)[NOUT]) {
-    const T tt = time / f.dt, xx = x / f.dx, yy = y / f.dy;
-    // clamp in floating point first: int conversion of huge / non-finite values is undefined
-    const int kk = (int)tmin(T(f.nt - 2), tmax(T(0), Real<T>::floor(tt)));
-    const int ii = (int)tmin(T(f.nx - 2), tmax(T(0), Real<T>::floor(xx)));
-    const int jj = (int)tmin(T(f.ny - 2), tmax(T(0), Real<T>::floor(yy)));
-    const T wt = tt - T(kk), wx = xx - T(ii), wy = yy - T(jj);
+    const FlowCell<T> c = flow_locate(f, time, x, y);
     const long row = (long)f.nx * f.nc, plane = (long)f.ny * row;
-    const T* p = f.field + (long)kk * plane + (long)jj * row + (long)ii * f.nc;
+    const T* p = f.field + (long)c.kk * plane + (long)c.jj * row + (long)c.ii * f.nc;
 #pragma unroll
-    for (int c = 0; c < NOUT; ++c) {
-        T acc = T(0);
-#pragma unroll
-        for (int dk = 0; dk < 2; ++dk) {
-            const T* q = p + dk * plane + c;
-            const T c00 = __ldg(q), c01 = __ldg(q + f.nc), c10 = __ldg(q + row), c11 = __ldg(q + row + f.nc);
-            const T r0 = c00 * (T(1) - wx) + c01 * wx;
-            const T r1 = c10 * (T(1) - wx) + c11 * wx;
-            acc += ((T(1) - wy) * r0 + wy * r1) * (dk == 0 ? (T(1) - wt) : wt);
-        }
-        res[c] = acc;
+    for (int k = 0; k < NOUT; ++k) {
+        const T* q = p + k;
+        res[k] = flow_blend(c, __ldg(q), __ldg(q + f.nc), __ldg(q + row), __ldg(q + row + f.nc),
+                            __ldg(q + plane), __ldg(q + plane + f.nc), __ldg(q + plane + row), __ldg(q + plane + row + f.nc));
     }
+}
+
+// The env's gather, nc = 2 (u, v interleaved): every corner is one 8-byte element and the two x-neighbours
+// are adjacent, so a cell is 4 rows of 16 contiguous bytes.  Each thread stages its rows into its own shared
+// memory slot with cp.async (LDGSTS: no register round trip, the copies stay in flight while the thread
+// works through the 30-float action ring), then blends from shared memory.
+#ifndef MVRL_AUV_STAGE_SMEM
+#define MVRL_AUV_STAGE_SMEM 1
+#endif
+#define MVRL_AUV_BLOCK 128
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// issue: 8 x 8-byte copies (2 time levels x 2 rows x 2 x-neighbours) into slot[8] of this thread
+__device__ __forceinline__ void flow_stage_issue(const FlowDev<float>& f, const FlowCell<float>& c, float2 (*slot)[MVRL_AUV_BLOCK]) {
+    const long row = (long)f.nx, plane = (long)f.ny * row;   // in float2 elements
+    const float2* p = reinterpret_cast<const float2*>(f.field) + (long)c.kk * plane + (long)c.jj * row + c.ii;
+#pragma unroll
+    for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int di = 0; di < 2; ++di) cp_async8(&slot[dk * 4 + dj * 2 + di][threadIdx.x], p + dk * plane + dj * row + di);
+}
+
+__device__ __forceinline__ void flow_stage_blend(const FlowCell<float>& c, float2 (*slot)[MVRL_AUV_BLOCK], float (&res)[2]) {
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = slot[k][threadIdx.x];
+    res[0] = flow_blend(c, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x);
+    res[1] = flow_blend(c, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y);
 }
 
 template <typename T> struct AuvDev {
@@ -110,22 +154,26 @@ __device__ __forceinline__ void draw_reset_auv(const AuvDev<T>& P, unsigned long
 }
 
 // K4: AuvEnv.step, verySimpleAuv.py:264-410
-template <typename T>
-__global__ void __launch_bounds__(128)
+// STAGE: the fp32 / 2-component gather goes through shared memory with cp.async (see flow_stage_issue)
+template <typename T, bool STAGE>
+__global__ void __launch_bounds__(MVRL_AUV_BLOCK)
 auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
+    __shared__ float2 stage[STAGE ? 8 : 1][MVRL_AUV_BLOCK];
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const AuvDev<T>& P = a.P;
     const long ld = a.ld;
     T x = a.state[i], y = a.state[ld + i], psi = a.state[2 * ld + i];
+    T heading_target = a.target[i], t_offset = a.target[ld + i];
+    const int istep = a.istep[i] + 1;
+    const T time = T(istep) * a.dt;
+    const FlowCell<T> cell = flow_locate(a.flow, time + t_offset, x, y);
+    if constexpr (STAGE) flow_stage_issue(a.flow, cell, stage);   // in flight while the rest of the inputs arrive
     T u = a.state[3 * ld + i], v = a.state[4 * ld + i], r = a.state[5 * ld + i];
     const T a0 = a.action[i], a1 = a.action[ld + i], a2 = a.action[2 * ld + i];
     T mm[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) mm[k] = a.mults[k * ld + i];
-    T heading_target = a.target[i], t_offset = a.target[ld + i];
-    const int istep = a.istep[i] + 1;
-    const T time = T(istep) * a.dt;
     bool is_done = istep >= a.max_steps;
 
     // recentActions.appendleft(action): ring slot, then statistics over the valid entries
@@ -149,7 +197,12 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     T sn, cs;
     Real<T>::sincos(psi, &sn, &cs);
     T cur[2];
-    flow_interp<T, 2>(a.flow, time + t_offset, x, y, cur);
+    if constexpr (STAGE) {
+        cp_async_wait_all();   // each thread reads back only what it copied itself: no barrier needed
+        flow_stage_blend(cell, stage, cur);
+    } else {
+        flow_interp<T, 2>(a.flow, time + t_offset, x, y, cur);
+    }
     const T dxv = u - cur[0], dyv = v - cur[1];
     const T vr0 = cs * dxv + sn * dyv, vr1 = -sn * dxv + cs * dyv;
     const T fh0 = (P.Xu * mm[5] + P.Xuu * mm[2] * tabs(vr0)) * vr0;

@@ -1,5 +1,6 @@
 // C ABI of the legacy path (K4): AuvEnv step/reset and ReconstructedFlow scale/interp.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -14,6 +15,7 @@ struct MvrlAuv {
     const void* field;
     int nt, ny, nx, nc;
     double dx, dy, dtf;
+    bool stage_smem;   // MVRL_AUV_NO_STAGE=1 in the environment selects the direct L2 gather instead
 };
 
 extern "C" MVRL_API int mvrl_auv_default_params(MvrlAuvParams* p) {
@@ -36,6 +38,7 @@ extern "C" MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* para
     MvrlAuv* h = new (std::nothrow) MvrlAuv();
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
     h->p = *params; h->c = *cfg; h->field = nullptr;
+    { const char* e = getenv("MVRL_AUV_NO_STAGE"); h->stage_smem = !(e && e[0] == '1'); }
     *out = h;
     return MVRL_OK;
 }
@@ -77,7 +80,14 @@ template <typename T> static int auv_step_impl(const MvrlAuv* h, int64_t n, int6
     a.episode = b->episode; a.term_obs = (T*)b->terminal_obs; a.aux = (T*)b->aux; a.stats = b->ep_stats;
     a.dt = T(h->c.dt); a.max_steps = h->c.max_steps; a.seed = h->c.seed; a.env_id0 = h->c.env_id0;
     a.auto_reset = h->c.auto_reset; a.stop_on_bounds = h->c.stop_on_bounds; a.apply_noise = h->c.apply_noise;
-    auv_step_kernel<T><<<mvrl_grid_for(n, 128), 128, 0, s>>>(a);
+    if constexpr (sizeof(T) == 4 && MVRL_AUV_STAGE_SMEM != 0) {
+        // staged gather needs the interleaved (u, v) field, 8-byte aligned
+        if (h->nc == 2 && (((uintptr_t)h->field) & 7u) == 0 && h->stage_smem) {
+            auv_step_kernel<T, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
+            return mvrl_check_launch("auv_step");
+        }
+    }
+    auv_step_kernel<T, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
     return mvrl_check_launch("auv_step");
 }
 

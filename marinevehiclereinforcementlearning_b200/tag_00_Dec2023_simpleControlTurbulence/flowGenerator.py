@@ -9,13 +9,29 @@ import torch
 from ..auv import FlowField
 
 
-def synthetic_base_field(lt_mean, nt, seed=7, sigma=0.05):
+def synthetic_base_field(lt_mean, nt, seed=7, sigma=0.05, kind="noise"):
     """Stand-in for the SPOD reconstruction when ``coeffs.npy`` / ``modes_r.npy`` are
-    unavailable (they are absent from the reference checkout): long-time mean +
-    seeded Gaussian fluctuations, ``[nt, Ny, Nx, 3]``."""
+    unavailable (they are absent from the reference checkout): long-time mean + seeded
+    fluctuations, ``[nt, Ny, Nx, 3]``.  ``kind="noise"``: white Gaussian noise of standard
+    deviation ``sigma``.  ``kind="modes"``: a handful of long-wave
+    travelling modes of amplitude ``sigma`` - like real turbulence data (and unlike white noise)
+    it extrapolates gently for x, y < 0, where ``interp`` reads because it ignores ``translate``."""
     rng = np.random.default_rng(seed)
     lt_mean = np.asarray(lt_mean, dtype=float)
-    return lt_mean[None] + sigma * rng.standard_normal((nt,) + lt_mean.shape)
+    if kind == "noise":
+        return lt_mean[None] + sigma * rng.standard_normal((nt,) + lt_mean.shape)
+    if kind != "modes":
+        raise ValueError("kind must be 'noise' or 'modes'")
+    ny, nx, nf = lt_mean.shape
+    t = np.arange(nt, dtype=np.float32)[:, None, None]
+    y = np.arange(ny, dtype=np.float32)[None, :, None]
+    x = np.arange(nx, dtype=np.float32)[None, None, :]
+    f = np.repeat(lt_mean[None].astype(np.float32), nt, axis=0)
+    for c in range(nf):
+        for _ in range(4):
+            kt, ky, kx = rng.uniform(0.05, 0.3), rng.uniform(0.02, 0.12), rng.uniform(0.02, 0.12)
+            f[..., c] += (0.4 * sigma) * np.sin(kt * t + ky * y + kx * x + rng.uniform(0, 2 * np.pi))
+    return f
 
 
 class ReconstructedFlow(FlowField):
@@ -65,7 +81,7 @@ class ReconstructedFlow(FlowField):
         return self
 
     @classmethod
-    def synthetic(cls, dataDir=None, lt_mean=None, nt=2000, seed=7, sigma=0.05, dtype=torch.float32, device="cuda"):
+    def synthetic(cls, dataDir=None, lt_mean=None, nt=2000, seed=7, sigma=0.05, kind="noise", dtype=torch.float32, device="cuda"):
         """Mean field (``ltm.npy`` of ``dataDir`` or ``lt_mean``) + seeded noise, ``nt`` time levels."""
         coords, dx, dy, dt = None, 0.005, 0.005, 0.002
         if lt_mean is None:
@@ -74,7 +90,7 @@ class ReconstructedFlow(FlowField):
             if os.path.exists(cpath):
                 coords = np.load(cpath)
                 dx, dy = cls._check_spacing(coords)
-        return cls.from_base_field(synthetic_base_field(lt_mean, nt, seed, sigma), baseDx=dx, baseDy=dy, baseDt=dt,
+        return cls.from_base_field(synthetic_base_field(lt_mean, nt, seed, sigma, kind), baseDx=dx, baseDy=dy, baseDt=dt,
                                    baseCoords=coords, lt_mean=np.asarray(lt_mean), dtype=dtype, device=device)
 
     # turbulence intensity on the plane, flowGenerator.py:47-51 (computed lazily: the env never needs it)

@@ -309,3 +309,27 @@ def test_step_host_and_step_range_match_step_bitwise():
             assert torch.equal(obs.cpu(), h_obs) and torch.equal(rew.cpu(), h_rew) and torch.equal(done.cpu(), h_done.bool())
             assert torch.equal(a._state, b._state) and torch.equal(a._state, c._state) and torch.equal(a._obs, c._obs)
             assert torch.equal(a._path, b._path) and torch.equal(a._path, c._path)
+
+
+def test_two_envs_per_thread_kernel_matches_one_env_kernel_bitwise(monkeypatch):
+    """fp32: the packed (F2, FFMA2) instantiation and the one-env-per-thread instantiation run the same
+    arithmetic per environment - bitwise equal states / observations, odd batch size, every action mode,
+    with auto-reset, for the accurate and the fast-math variants."""
+    n, steps = 4097, 12
+    for mode, na, scale in (("rpm", 8, 3500.0), ("force", 6, 40.0), ("setpoint", 6, 1.0)):
+        for fast in (False, True):
+            rng = np.random.default_rng(51)
+            acts = torch.as_tensor(rng.uniform(-scale, scale, (steps, n, na)), dtype=torch.float32, device=DEV)
+            kw = dict(action_mode=mode, dtype=torch.float32, device=DEV, maxSteps=5, auto_reset=True, seed=3, fast_math=fast)
+            monkeypatch.setenv("MVRL_NO_X2", "0")
+            packed = BlueROV2Heavy6DoFVecEnv(n, **kw)
+            packed.reset()
+            monkeypatch.setenv("MVRL_NO_X2", "1")
+            single = BlueROV2Heavy6DoFVecEnv(n, **kw)
+            single.reset()
+            for k in range(steps):
+                op, _, dp, _ = packed.step(acts[k])
+                os_, _, ds, _ = single.step(acts[k])
+                assert torch.equal(op, os_) and torch.equal(dp, ds), (mode, fast, k)
+                assert torch.equal(packed._state, single._state) and torch.equal(packed._ctrl, single._ctrl), (mode, fast, k)
+            assert packed.episode_stats() == single.episode_stats()
