@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int j = 0; j < CHAINS; ++j) x[j] = x[j] * a + b;
+            for (int j = 0; j < CHAINS; ++j) x[j] = fmaf_t(x[j], a, b);   // explicit: this unit is built with -fmad=false
         }
     }
     T s = T(0);

@@ -186,8 +186,8 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         } else {  // 6DoF.py:545-552
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                sp[k] = act[k] * V(P.act_pos) + y[k];
-                sp[3 + k] = act[3 + k] * V(P.act_ang) + y[3 + k];
+                sp[k] = fmaf_t(act[k], V(P.act_pos), y[k]);
+                sp[3 + k] = fmaf_t(act[3 + k], V(P.act_ang), y[3 + k]);
             }
         }
 #pragma unroll
@@ -261,12 +261,16 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                     const V d0 = V(cp) * k[3], d1 = V(cp) * k[4], d2 = V(cp) * k[5];
                     const V z0 = d0 * d0, z1 = d1 * d1, z2 = d2 * d2;
                     const V zs = z0 + z1 + z2;
-                    if (!vany(vgt(zs, V(MVRL_TRIG_DELTA_MAX2)))) {   // (NaN offsets take the cheap path and stay NaN)
-                        sincos_delta(g0.sph, g0.cph, d0, z0, &g.sph, &g.cph);
-                        sincos_delta(g0.sth, g0.cth, d1, z1, &g.sth, &g.cth);
-                        sincos_delta(g0.sps, g0.cps, d2, z2, &g.sps, &g.cps);
-                    } else {
-                        g = trig6<V, FAST>(yt[3], yt[4], yt[5]);
+                    sincos_delta(g0.sph, g0.cph, d0, z0, &g.sph, &g.cph);
+                    sincos_delta(g0.sth, g0.cth, d1, z1, &g.sth, &g.cth);
+                    sincos_delta(g0.sps, g0.cps, d2, z2, &g.sps, &g.cps);
+                    const auto big = vgt(zs, V(MVRL_TRIG_DELTA_MAX2));   // (NaN offsets stay on the cheap path and stay NaN)
+                    if (vany(big)) {   // rare: an environment with a large offset gets the full evaluation - decided per
+                                       // environment, so a result never depends on which environment shares the thread
+                        const Trig6<V> gf = trig6<V, FAST>(yt[3], yt[4], yt[5]);
+                        g.sph = vsel(big, gf.sph, g.sph); g.cph = vsel(big, gf.cph, g.cph);
+                        g.sth = vsel(big, gf.sth, g.sth); g.cth = vsel(big, gf.cth, g.cth);
+                        g.sps = vsel(big, gf.sps, g.sps); g.cps = vsel(big, gf.cps, g.cps);
                     }
                 }
             } else {

@@ -156,33 +156,36 @@ __device__ __forceinline__ void thrust_wrench(const Rov6Dev<S>& P, const V (&F)[
 // sign(c_i) sqrt(|c_i| / (rho D^4 Kt)) 60.
 template <typename V, bool SP, typename S>
 __device__ __forceinline__ void allocate_demand(const Rov6Dev<S>& P, const Trig6<V>& g, const V (&gcf)[6], V (&c)[8]) {
-    const V ix = g.cth * g.cps, iy = g.cph * g.sps + g.sph * g.sth * g.cps, iz = g.sph * g.sps - g.cph * g.sth * g.cps;
-    const V jx = -(g.cth * g.sps), jy = g.cph * g.cps - g.sph * g.sth * g.sps, jz = g.sph * g.cps + g.cph * g.sth * g.sps;
+    // body axes of R = Rx(phi) Ry(theta) Rz(psi); every FMA is written out (the translation unit is compiled
+    // with -fmad=false so that the one- and two-environment instantiations execute the same operations)
+    const V ss = g.sph * g.sth, cs = g.cph * g.sth;
+    const V ix = g.cth * g.cps, iy = fmaf_t(ss, g.cps, g.cph * g.sps), iz = fmaf_t(-cs, g.cps, g.sph * g.sps);
+    const V jx = -(g.cth * g.sps), jy = fmaf_t(-ss, g.sps, g.cph * g.cps), jz = fmaf_t(cs, g.sps, g.sph * g.cps);
     const V kx = g.sth, ky = -(g.sph * g.cth), kz = g.cph * g.cth;
     V b[6];
-    b[0] = gcf[0] * ix + gcf[1] * iy + gcf[2] * iz;
-    b[1] = gcf[0] * jx + gcf[1] * jy + gcf[2] * jz;
-    b[2] = gcf[0] * kx + gcf[1] * ky + gcf[2] * kz;
-    b[3] = gcf[3] * ix + gcf[4] * iy + gcf[5] * iz;
-    b[4] = gcf[3] * jx + gcf[4] * jy + gcf[5] * jz;
-    b[5] = gcf[3] * kx + gcf[4] * ky + gcf[5] * kz;
+    b[0] = fmaf_t(gcf[2], iz, fmaf_t(gcf[1], iy, gcf[0] * ix));
+    b[1] = fmaf_t(gcf[2], jz, fmaf_t(gcf[1], jy, gcf[0] * jx));
+    b[2] = fmaf_t(gcf[2], kz, fmaf_t(gcf[1], ky, gcf[0] * kx));
+    b[3] = fmaf_t(gcf[5], iz, fmaf_t(gcf[4], iy, gcf[3] * ix));
+    b[4] = fmaf_t(gcf[5], jz, fmaf_t(gcf[4], jy, gcf[3] * jx));
+    b[5] = fmaf_t(gcf[5], kz, fmaf_t(gcf[4], ky, gcf[3] * kx));
     if constexpr (SP) {
         // pinv of the default A: horizontals see (X, Y, N) only, verticals see (Z, K, M) only
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c[i] = V(P.Ainv[i][0]) * b[0] + V(P.Ainv[i][1]) * b[1] + V(P.Ainv[i][5]) * b[5];
+        for (int i = 0; i < 4; ++i) c[i] = fmaf_t(V(P.Ainv[i][5]), b[5], fmaf_t(V(P.Ainv[i][1]), b[1], V(P.Ainv[i][0]) * b[0]));
 #pragma unroll
         for (int i = 4; i < 8; ++i) {
-            V s = V(S(0));
+            V s = V(P.Ainv[i][0]) * b[0];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) s += V(P.Ainv[i][k]) * b[k];
+            for (int k = 1; k < 5; ++k) s = fmaf_t(V(P.Ainv[i][k]), b[k], s);
             c[i] = s;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            V s = V(S(0));
+            V s = V(P.Ainv[i][0]) * b[0];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s += V(P.Ainv[i][k]) * b[k];
+            for (int k = 1; k < 6; ++k) s = fmaf_t(V(P.Ainv[i][k]), b[k], s);
             c[i] = s;
         }
     }
@@ -415,9 +418,9 @@ __device__ __forceinline__ void pid6(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_i
     for (int k = 0; k < 6; ++k) {
         const V eo = vsel(none, e[k], e_old[k]);
         const V dedt = (e[k] - eo) * V(inv_dt);
-        V ei = e_int[k] + V(S(0.5)) * (eo + e[k]) * V(dtc);
+        V ei = fmaf_t(V(S(0.5) * dtc), eo + e[k], e_int[k]);
         ei = vsel(vgt(tabs(e[k]), V(P.pWind[k])), V(S(0)), ei);
-        const V cvl = V(P.pKp[k]) * e[k] + V(P.pKd[k]) * dedt + V(P.pKi[k]) * ei;
+        const V cvl = fmaf_t(V(P.pKi[k]), ei, fmaf_t(V(P.pKd[k]), dedt, V(P.pKp[k]) * e[k]));
         out[k] = tmax(V(-P.pMax[k]), tmin(V(P.pMax[k]), cvl));
         e_int[k] = ei;
         e_old[k] = e[k];

@@ -55,8 +55,10 @@ class BlueROV2Heavy6DoF_PID_controller(object):
         d_ctrl = _col(ctrl, dev)
         out = torch.empty((6, 1), dtype=_F64, device=dev)
         h = self._handle
-        _lib.check(h.lib.mvrl_rov6_pid(h._h, 1, 1, _lib.ptr(_col([x, y, z, phi, theta, psi], dev)), _lib.ptr(_col([t], dev)),
-                                       _lib.ptr(_col(self.setPoint, dev)), _lib.ptr(d_ctrl), _lib.ptr(out), _lib.current_stream(dev)))
+        # named tensors: a temporary would be freed (and its block reused by the next one) before the kernel reads it
+        d_pose, d_t, d_sp = _col([x, y, z, phi, theta, psi], dev), _col([t], dev), _col(self.setPoint, dev)
+        _lib.check(h.lib.mvrl_rov6_pid(h._h, 1, 1, _lib.ptr(d_pose), _lib.ptr(d_t), _lib.ptr(d_sp), _lib.ptr(d_ctrl), _lib.ptr(out),
+                                       _lib.current_stream(dev)))
         c = d_ctrl[:, 0].cpu().numpy()
         self.eOld, self.eInt, self.tOld = c[0:6].copy(), c[6:12].copy(), float(c[12])
         return out[:, 0].cpu().numpy()
@@ -110,14 +112,16 @@ class BlueROV2Heavy6DoF(Rov6Constants):
         self.rotation_angles = np.asarray(rotation_angles, dtype=float)
         dev = self._eval("rpm").device
         out = torch.empty((9, 1), dtype=_F64, device=dev)
-        _lib.check(_lib.load().mvrl_body_axes(_lib.F64, 1, 1, _lib.ptr(_col(self.rotation_angles, dev)), _lib.ptr(out), _lib.current_stream(dev)))
+        d_ang = _col(self.rotation_angles, dev)
+        _lib.check(_lib.load().mvrl_body_axes(_lib.F64, 1, 1, _lib.ptr(d_ang), _lib.ptr(out), _lib.current_stream(dev)))
         self.iHat, self.jHat, self.kHat = out[:, 0].cpu().numpy().reshape(3, 3)
 
     def _rotate(self, vec, to_vehicle):
         dev = self._eval("rpm").device
         axes = _col(np.concatenate([self.iHat, self.jHat, self.kHat]), dev)
         out = torch.empty((3, 1), dtype=_F64, device=dev)
-        _lib.check(_lib.load().mvrl_frame_rotate(_lib.F64, 1, 1, _lib.ptr(axes), _lib.ptr(_col(vec, dev)), _lib.ptr(out), int(to_vehicle),
+        d_vec = _col(vec, dev)
+        _lib.check(_lib.load().mvrl_frame_rotate(_lib.F64, 1, 1, _lib.ptr(axes), _lib.ptr(d_vec), _lib.ptr(out), int(to_vehicle),
                                                  _lib.current_stream(dev)))
         return out[:, 0].cpu().numpy()
 
