@@ -251,6 +251,10 @@ MVRL_API int mvrl_rov3_reset(MvrlRov3* h, int64_t n, int64_t ld, const MvrlRov3B
 MVRL_API int mvrl_rov3_thruster_model(MvrlRov3* h, int64_t n, const void* u, const void* rpm, void* F, void* X,
                                       mvrl_stream_t stream);
 
+/* LOSNavigation.predict / lineOfSight (3DoF.py:517-607), the heuristic agent in front of the 3DoF env:
+ * obs T [5][ld] (way-points relative to the vehicle, heading error) -> action T [3][ld]; rnav = 0.5 upstream */
+MVRL_API int mvrl_los_navigation(int dtype, int64_t n, int64_t ld, const void* obs, void* action, double rnav, mvrl_stream_t stream);
+
 /* -------------------------------------------------------------- legacy -- */
 
 /* AuvEnv constants, tag_00.../verySimpleAuv.py:110-132 */
@@ -304,6 +308,15 @@ MVRL_API int mvrl_flow_interp(int dtype, const void* field, int nt, int ny, int 
 /* ReconstructedFlow.scale on the values (flowGenerator.py:80-90): base T [cells][3] -> out T [cells][nc_out] */
 MVRL_API int mvrl_flow_scale(int dtype, int64_t cells, const void* base, void* out, int nc_out, double velocityScale,
                              double turbScale, mvrl_stream_t stream);
+
+/* CustomReplayBuffer.add (tag_00.../main_02_sbl_contrib_customBuffer.py:57-160): stores the batch of transitions and its
+ * mirror images.  obs / next_obs T [11][ld], act T [3][ld], reward T [n], done [n] (SoA, as the env holds them) ->
+ * buf_obs / buf_next_obs T [buffer_size][n][11], buf_act T [buffer_size][n][3], buf_reward T [buffer_size][n],
+ * buf_done [buffer_size][n]; transformation t (0 = identity ... 4) goes to slot (pos + t) % buffer_size, t < n_transforms. */
+MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t ld, const void* obs, const void* next_obs, const void* act,
+                                       const void* reward, const uint8_t* done, void* buf_obs, void* buf_next_obs, void* buf_act,
+                                       void* buf_reward, uint8_t* buf_done, int64_t buffer_size, int64_t pos, int n_transforms,
+                                       mvrl_stream_t stream);
 
 /* ------------------------------------------------------------ calibration -- */
 /* K6: measured FMA throughput of the FP32 / FP64 pipe in TFLOP/s (2 flop per FMA,

@@ -109,6 +109,7 @@ PROTOTYPES = {
     "mvrl_rov3_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov3Buffers), _vp]),
     "mvrl_rov3_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov3Buffers), _vp, C.POINTER(_d), _vp]),
     "mvrl_rov3_thruster_model": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mvrl_los_navigation": (_int, [_int, _i64, _i64, _vp, _vp, _d, _vp]),
     "mvrl_auv_default_params": (_int, [C.POINTER(MvrlAuvParams)]),
     "mvrl_auv_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlAuvParams), C.POINTER(MvrlAuvConfig)]),
     "mvrl_auv_destroy": (_int, [_vp]),
@@ -116,6 +117,7 @@ PROTOTYPES = {
     "mvrl_auv_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp]),
     "mvrl_auv_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp, _vp, _vp]),
     "mvrl_flow_interp": (_int, [_int, _vp, _int, _int, _int, _int, _d, _d, _d, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mvrl_replay_add_symmetric": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "mvrl_flow_scale": (_int, [_int, _i64, _vp, _vp, _int, _d, _d, _vp]),
 }
 

@@ -23,10 +23,12 @@ template <typename T>
 __device__ __forceinline__ FlowCell<T> flow_locate(const FlowDev<T>& f, T time, T x, T y) {
     const T tt = time / f.dt, xx = x / f.dx, yy = y / f.dy;
     FlowCell<T> c;
-    // clamp in floating point first: int conversion of huge / non-finite values is undefined
-    c.kk = (int)tmin(T(f.nt - 2), tmax(T(0), Real<T>::floor(tt)));
-    c.ii = (int)tmin(T(f.nx - 2), tmax(T(0), Real<T>::floor(xx)));
-    c.jj = (int)tmin(T(f.ny - 2), tmax(T(0), Real<T>::floor(yy)));
+    // clamp in floating point first: int conversion of huge / non-finite values is undefined.  fmin / fmax
+    // return the non-NaN operand, so a NaN coordinate (a vehicle that diverged) indexes cell 0 and yields NaN
+    // weights instead of an out-of-bounds gather (upstream raises on int(floor(nan))).
+    c.kk = (int)fmin(T(f.nt - 2), fmax(T(0), Real<T>::floor(tt)));
+    c.ii = (int)fmin(T(f.nx - 2), fmax(T(0), Real<T>::floor(xx)));
+    c.jj = (int)fmin(T(f.ny - 2), fmax(T(0), Real<T>::floor(yy)));
     c.wt = tt - T(c.kk); c.wx = xx - T(c.ii); c.wy = yy - T(c.jj);
     return c;
 }
@@ -354,6 +356,39 @@ __global__ void flow_scale_kernel(long cells, const T* base, T* out, int nc_out,
     out[nc_out * i] = u;
     out[nc_out * i + 1] = v;
     if (nc_out == 3) out[3 * i + 2] = base[3 * i + 2] / tmax(T(1e-6), (vel * turb) * (vel * turb));
+}
+
+// ---------------------------------------------------------------------------
+// CustomReplayBuffer.add (tag_00.../main_02_sbl_contrib_customBuffer.py:57-160): every transition of the
+// legacy env is stored together with its mirror images (obs / action sign flips); reward and done are
+// unchanged.  Slot (pos + t) % buffer_size holds transformation t of the whole batch, as upstream.
+// obs, next_obs T [11][ld], act T [3][ld] (SoA, straight from the env) -> buffers [buffer_size][n][k] (AoS rows,
+// the layout a learner samples).  One thread per (environment, transformation).
+// ---------------------------------------------------------------------------
+__constant__ float kReplaySignObs[5][11] = {
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, {-1, -1, 1, 1, -1, -1, -1, -1, 1, 1, 1}, {-1, 1, 1, 1, -1, 1, -1, 1, 1, 1, 1},
+    {1, -1, 1, 1, 1, -1, 1, -1, 1, 1, 1}, {1, 1, -1, 1, 1, 1, 1, 1, -1, 1, 1}};
+__constant__ float kReplaySignAct[5][3] = {{1, 1, 1}, {-1, -1, 1}, {-1, 1, 1}, {1, -1, 1}, {1, 1, -1}};
+
+template <typename T>
+__global__ void replay_add_symmetric_kernel(long n, long ld, const T* obs, const T* next_obs, const T* act, const T* reward,
+                                            const uint8_t* done, T* b_obs, T* b_next, T* b_act, T* b_rew, uint8_t* b_done,
+                                            long buffer_size, long pos, int n_transforms) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * n_transforms) return;
+    const int t = (int)(e / n);
+    const long i = e - (long)t * n;
+    const long row = ((pos + t) % buffer_size) * n + i;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        const T sg = T(kReplaySignObs[t][k]);
+        b_obs[row * 11 + k] = obs[k * ld + i] * sg;
+        b_next[row * 11 + k] = next_obs[k * ld + i] * sg;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b_act[row * 3 + k] = act[k * ld + i] * T(kReplaySignAct[t][k]);
+    b_rew[row] = reward[i];
+    b_done[row] = done[i];
 }
 
 }  // namespace mvrl

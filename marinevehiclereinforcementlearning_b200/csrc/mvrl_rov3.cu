@@ -167,3 +167,14 @@ extern "C" MVRL_API int mvrl_rov3_thruster_model(MvrlRov3* h, int64_t n, const v
     else rov3_thruster_kernel<float><<<mvrl_grid_for(n, 128), 128, 0, s>>>(h->pf, n, (const float*)u, (const float*)rpm, (float*)F, (float*)X);
     return mvrl_check_launch("rov3_thruster_model");
 }
+
+// LOSNavigation.predict for n observations (3DoF.py:586-607)
+extern "C" MVRL_API int mvrl_los_navigation(int dtype, int64_t n, int64_t ld, const void* obs, void* action, double rnav, mvrl_stream_t stream) {
+    if (!obs || !action || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_los_navigation: bad argument");
+    if (n == 0) return MVRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) los_navigation_kernel<double><<<mvrl_grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)obs, (double*)action, rnav);
+    else if (dtype == MVRL_F32) los_navigation_kernel<float><<<mvrl_grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)obs, (float*)action, (float)rnav);
+    else return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    return mvrl_check_launch("los_navigation");
+}

@@ -355,6 +355,51 @@ rov3_reset_kernel(const __grid_constant__ Rov3ResetArgs<T> a) {
     for (int k = 0; k < 5; ++k) a.obs[k * ld + i] = obs[k];
 }
 
+// ---------------------------------------------------------------------------
+// lineOfSight + LOSNavigation.predict (3DoF.py:517-607): the heuristic agent that turns the 5
+// observations of the 3DoF env into its 3 actions.  Branch order and NaN behaviour as upstream.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void line_of_sight(T p0x, T p0y, T p1x, T p1y, T rnav, T* tx, T* ty) {
+    const T d_to_wp = Real<T>::sqrt(p1x * p1x + p1y * p1y);
+    if (d_to_wp < rnav) { *tx = p1x; *ty = p1y; return; }
+    const T vx = p1x - p0x, vy = p1y - p0y;
+    const T d_seg = Real<T>::sqrt(vx * vx + vy * vy);
+    const T hx = vx / d_seg, hy = vy / d_seg;
+    const T det = p0x * p1y - p1x * p0y;
+    const T delta = rnav * rnav * (d_seg * d_seg) - det * det;
+    if (delta < T(0)) {  // the segment is out of sight: head for the nearest point of it
+        const T d_along = (-p0x) * hx + (-p0y) * hy;
+        if (d_along > d_seg) { *tx = p1x; *ty = p1y; }
+        else if (d_along < T(0)) { *tx = p0x; *ty = p0y; }
+        else { *tx = p0x + d_along * hx; *ty = p0y + d_along * hy; }
+        return;
+    }
+    if (!(delta >= T(0))) { *tx = Real<T>::nan(); *ty = Real<T>::nan(); return; }  // NaN input (upstream: unbound variable)
+    T sy = sgn(vy);
+    if (tabs(sy) < T(1e-12)) sy = T(1);
+    const T lim = tmax(T(1e-6), d_seg);
+    const T den = lim * lim, sq = Real<T>::sqrt(delta);
+    const T a0x = (det * vy + sy * vx * sq) / den, a0y = (-det * vx + tabs(vy) * sq) / den;
+    const T a1x = (det * vy - sy * vx * sq) / den, a1y = (-det * vx - tabs(vy) * sq) / den;
+    const T s0 = (hx * (a0x - p0x) + hy * (a0y - p0y)) / lim;
+    const T s1 = (hx * (a1x - p0x) + hy * (a1y - p0y)) / lim;
+    if (s0 >= T(0) && s0 <= T(1) && s0 > s1) { *tx = a0x; *ty = a0y; }
+    else if (s1 >= T(0) && s1 <= T(1)) { *tx = a1x; *ty = a1y; }
+    else if (d_to_wp < Real<T>::sqrt(p0x * p0x + p0y * p0y)) { *tx = p1x; *ty = p1y; }
+    else { *tx = p0x; *ty = p0y; }
+}
+
+// obs T [5][ld] -> action T [3][ld]
+template <typename T>
+__global__ void los_navigation_kernel(long n, long ld, const T* obs, T* action, T rnav) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T tx, ty;
+    line_of_sight(obs[i], obs[ld + i], obs[2 * ld + i], obs[3 * ld + i], rnav, &tx, &ty);
+    action[i] = tx; action[ld + i] = ty; action[2 * ld + i] = obs[4 * ld + i];
+}
+
 template <typename T>
 __global__ void rov3_thruster_kernel(const Rov3Dev<T> P, long n, const T* u, const T* rpm, T* F, T* X) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

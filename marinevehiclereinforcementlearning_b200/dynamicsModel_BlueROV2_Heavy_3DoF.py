@@ -6,8 +6,8 @@ in / numpy out, old-Gym 4-tuple), plus ``BlueROV2Heavy3DoFVecEnv`` for batches.
 Every number is produced by the CUDA kernels of libmvrl (fp64, one
 environment); this file only marshals.  As for the 6DoF module, ``env.step``
 integrates with fixed-step RK4 x ``nSub`` instead of scipy's adaptive RK45.
-The LOS navigation / plotting helpers of the reference module are out of scope
-(SURVEY.md section 2, row 10).
+``lineOfSight`` / ``LOSNavigation`` (3DoF.py:517-607) run as the ``mvrl_los_navigation`` kernel; the plotting
+helpers of the reference module are out of scope.
 """
 import numpy as np
 import torch
@@ -157,3 +157,43 @@ class BlueROV2Heavy3DoFEnv(Env):
         else:
             self.steps_beyond_done = 0
         return self.state, reward, done, {}
+
+
+def _los_actions(obs_fm, rnav):
+    """[5, N] CUDA tensor -> [3, N] actions through ``mvrl_los_navigation``."""
+    n = obs_fm.shape[1]
+    act = torch.empty((3, n), dtype=obs_fm.dtype, device=obs_fm.device)
+    _lib.check(_lib.load().mvrl_los_navigation(_lib.torch_dtype_code(obs_fm.dtype), n, n, _lib.ptr(obs_fm), _lib.ptr(act), float(rnav),
+                                               _lib.current_stream(obs_fm.device)))
+    return act
+
+
+def lineOfSight(p0, p1, Rnav):
+    """3DoF.py:517-583: target point on the path segment p0 -> p1 (relative to the vehicle) within the
+    line-of-sight radius.  numpy 2-vectors in, numpy 2-vector out."""
+    _lib.require_cuda()
+    obs = torch.as_tensor(np.concatenate([np.asarray(p0, float), np.asarray(p1, float), [0.]]).reshape(5, 1), device="cuda")
+    return _los_actions(obs, Rnav)[:2, 0].cpu().numpy()
+
+
+class LOSNavigation(object):
+    """3DoF.py:586-607: SB3-like ``predict(obs, deterministic)`` -> (actions, states).  One observation
+    ``(5,)`` (numpy, like the reference) or a batch: numpy / torch ``[N, 5]`` -> ``[N, 3]`` (torch stays on the device)."""
+    Rnav = 0.5
+
+    def __init__(self):
+        pass
+
+    def predict(self, obs, deterministic=True):
+        states = obs
+        _lib.require_cuda()
+        if isinstance(obs, torch.Tensor):
+            o = obs if obs.is_cuda else obs.cuda()
+            single = o.dim() == 1
+            fm = o.reshape(-1, 5).T.contiguous()
+            act = _los_actions(fm, self.Rnav).T
+            return (act[0] if single else act), states
+        o = np.asarray(obs, dtype=np.float64)
+        fm = torch.as_tensor(np.ascontiguousarray(o.reshape(-1, 5).T), device="cuda")
+        act = _los_actions(fm, self.Rnav).T.cpu().numpy()
+        return (act[0] if o.ndim == 1 else act), states

@@ -1,7 +1,7 @@
 """Drop-in for the numerical helpers of the reference's ``resources.py``
 (``computeThrustAllocation`` :19-35, ``angleError`` :75-95,
-``coordinateTransform`` :98-143).  The plotting / SB3 glue of that file is out
-of scope.
+``coordinateTransform`` :98-143) and its evaluation loop (``evaluate_agent`` :145-198).  The plotting /
+SB3 training glue of that file is out of scope.
 
 ``angleError`` and ``coordinateTransform`` run as CUDA kernels
 (``mvrl_angle_error`` / ``mvrl_coordinate_transform``): scalars in -> numpy
@@ -82,3 +82,11 @@ def coordinateTransform(phi, theta, psi, dof=["x", "y", "psi"]):
         return J
     J = J.cpu().numpy()
     return J[0] if scalar else J
+
+
+def evaluate_agent(agent, env, num_episodes=1, num_steps=None, deterministic=True, num_last_for_reward=None,
+                   render=False, init=None, saveDir=None):
+    """resources.py:145-198 (see ``vec_tools.evaluate_agent``)."""
+    from .vec_tools import evaluate_agent as _impl
+    return _impl(agent, env, num_episodes=num_episodes, num_steps=num_steps, deterministic=deterministic,
+                 num_last_for_reward=num_last_for_reward, render=render, init=init, saveDir=saveDir)

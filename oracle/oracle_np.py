@@ -953,3 +953,46 @@ class AuvEnvOracle:
             self._install(idx, *self._draw(idx, True))
             obs[idx] = self.observe()[idx]  # only the reset envs: the others keep the obs taken before herr_o / perr_o moved on
         return obs, reward, done, info
+
+
+# ==========================================================================
+# action producers in front of the env step: LOS navigation (3DoF.py:517-607)
+# ==========================================================================
+def line_of_sight(p0, p1, rnav):
+    """``lineOfSight`` (3DoF.py:517-583), vectorised: p0, p1 [N, 2] way-points relative to the vehicle,
+    rnav [N] or scalar -> target point [N, 2].  Branch order and NaN behaviour (all comparisons false) as
+    in the reference."""
+    p0 = np.atleast_2d(np.asarray(p0, dtype=float)); p1 = np.atleast_2d(np.asarray(p1, dtype=float))
+    rnav = np.broadcast_to(np.asarray(rnav, dtype=float), p0.shape[:1])
+    with np.errstate(all="ignore"):
+        d_to_wp = np.sqrt(np.sum(p1 ** 2., axis=1))
+        path = p1 - p0
+        d_seg = np.sqrt(np.sum(path ** 2., axis=1))
+        p_hat = path / d_seg[:, None]                      # np.linalg.norm(pathVec): same value as dSegment
+        det = p0[:, 0] * p1[:, 1] - p1[:, 0] * p0[:, 1]
+        delta = rnav ** 2. * d_seg ** 2. - det ** 2.
+        # delta < 0: project the vehicle onto the segment
+        d_along = np.sum(-p0 * p_hat, axis=1)
+        t_neg = np.where((d_along > d_seg)[:, None], p1, np.where((d_along < 0)[:, None], p0, p0 + d_along[:, None] * p_hat))
+        # delta >= 0: the two intersections of the LOS circle with the line
+        sy = np.sign(path[:, 1]); sy = np.where(np.abs(sy) < 1e-12, 1., sy)
+        den = np.maximum(1e-6, d_seg) ** 2.
+        sq = np.sqrt(delta)
+        pp0 = np.stack([(det * path[:, 1] + sy * path[:, 0] * sq) / den, (-det * path[:, 0] + np.abs(path[:, 1]) * sq) / den], axis=1)
+        pp1 = np.stack([(det * path[:, 1] - sy * path[:, 0] * sq) / den, (-det * path[:, 0] - np.abs(path[:, 1]) * sq) / den], axis=1)
+        s0 = np.sum(p_hat * (pp0 - p0), axis=1) / np.maximum(1e-6, d_seg)
+        s1 = np.sum(p_hat * (pp1 - p0), axis=1) / np.maximum(1e-6, d_seg)
+        n0, n1 = np.sqrt(np.sum(p0 ** 2., axis=1)), np.sqrt(np.sum(p1 ** 2., axis=1))
+        t_pos = np.where(((s0 >= 0.) & (s0 <= 1.) & (s0 > s1))[:, None], pp0,
+                         np.where(((s1 >= 0.) & (s1 <= 1.))[:, None], pp1, np.where((n1 < n0)[:, None], p1, p0)))
+        # the reference tests `delta < 0` and `delta >= 0` separately: NaN delta leaves targetPoint unassigned
+        # (UnboundLocalError upstream); the build returns NaN there
+        t_far = np.where((delta < 0)[:, None], t_neg, np.where((delta >= 0)[:, None], t_pos, np.nan))
+        return np.where((d_to_wp < rnav)[:, None], p1, t_far)
+
+
+def los_navigation_predict(obs, rnav=0.5):
+    """``LOSNavigation.predict`` (3DoF.py:586-607): obs [N, 5] -> actions [N, 3] = (target point, heading error)."""
+    obs = np.atleast_2d(np.asarray(obs, dtype=float))
+    tp = line_of_sight(obs[:, 0:2], obs[:, 2:4], rnav)
+    return np.concatenate([tp, obs[:, 4:5]], axis=1)

@@ -180,3 +180,25 @@ def test_batched_vs_oracle_auto_reset_sharding_and_fp32():
             assert np.abs(o32.cpu().numpy() - ro)[same].max() < 1e-4 and np.abs(r32.cpu().numpy() - rr)[same].max() < 2e-3
     st = full.episode_stats()
     assert st["episodes"] == n_term and st["nonfinite"] == 0 and st["max_return"] <= 3.0 * 15
+
+
+def test_non_finite_positions_do_not_fault():
+    """A diverged vehicle (NaN / inf position) must not turn into an out-of-bounds gather."""
+    g = load_golden("legacy")
+    for dtype in (torch.float32, torch.float64):
+        flow, _ = make_flows(g, dtype)
+        env = AuvVecEnv(64, flow, dtype=dtype, maxSteps=10, auto_reset=False, stopOnBoundsExceeded=False)
+        env.reset()
+        env._state[0, :8] = float("nan")
+        env._state[1, 8:16] = float("inf")
+        env._state[0, 16:24] = -float("inf")
+        env._state[1, 24:32] = 3.0e38 if dtype == torch.float32 else 1.0e300
+        for _ in range(3):
+            obs, rew, done, _ = env.step(torch.zeros((64, 3), dtype=dtype, device=DEV))
+        torch.cuda.synchronize()
+        assert torch.isfinite(obs[32:]).all() and not torch.isfinite(env._state[:, :8]).all()
+        t = torch.tensor([0.1, float("nan"), float("inf")], dtype=dtype, device=DEV)
+        xy = torch.tensor([[float("nan"), 0.2], [0.1, 0.1], [-float("inf"), 0.3]], dtype=dtype, device=DEV)
+        out = flow.interp(t, xy)
+        torch.cuda.synchronize()
+        assert out.shape == (3, 3)

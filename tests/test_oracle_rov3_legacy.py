@@ -128,3 +128,10 @@ def test_auv_episodes():
             assert np.abs(last["terms"][0] - h[21:26]).max() < 1e-10
             if d[0]:
                 break
+
+
+def test_los_navigation_oracle_vs_reference_golden():
+    g = load_golden("agents")
+    t = o.line_of_sight(g["los_p0"], g["los_p1"], g["los_rnav"])
+    assert np.abs(t - g["los_target"]).max() < 1e-14 and not np.isnan(t).any()
+    assert np.abs(o.los_navigation_predict(g["nav_obs"]) - g["nav_action"]).max() < 1e-14

@@ -165,3 +165,34 @@ def test_auto_reset_and_sharding_bitwise():
             assert np.abs(full.path.cpu().numpy().reshape(n, 4) - ref.path).max() < 1e-12
     st = full.episode_stats()
     assert st["episodes"] == n * (steps // 4) and st["mean_length"] == 4.0 and st["nonfinite"] == 0
+
+
+def test_los_navigation_vs_reference_golden():
+    """lineOfSight / LOSNavigation.predict (3DoF.py:517-607) through mvrl_los_navigation."""
+    g = load_golden("agents")
+    nav = m3.LOSNavigation()
+    nav_obs = g["nav_obs"]
+    act, states = nav.predict(nav_obs)
+    assert act.shape == (500, 3) and np.abs(act - g["nav_action"]).max() < 1e-13 and states is nav_obs
+    a1, _ = nav.predict(g["nav_obs"][7])
+    assert a1.shape == (3,) and np.abs(a1 - g["nav_action"][7]).max() < 1e-13
+    for i in (0, 60, 90, 170, 210, 300, 2999):   # each branch family of the generator
+        t = m3.lineOfSight(g["los_p0"][i], g["los_p1"][i], float(g["los_rnav"][i]))
+        assert np.abs(t - g["los_target"][i]).max() < 1e-13, i
+    # batched on the device, all 3000 cases at Rnav = 0.5 vs the oracle, fp64 and fp32
+    obs = np.concatenate([g["los_p0"], g["los_p1"], np.zeros((3000, 1))], axis=1)
+    want = o.los_navigation_predict(obs, 0.5)
+    got, _ = nav.predict(torch.as_tensor(obs, device=DEV))
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-12
+    got32, _ = nav.predict(torch.as_tensor(obs, device=DEV, dtype=torch.float32))
+    close = np.abs(got32.cpu().numpy() - want).max(axis=1) < 1e-4      # fp32 may take the other branch at a tie
+    assert close.mean() > 0.995
+    # closing the loop: the heuristic drives the batched 3DoF env along its path
+    env = BlueROV2Heavy3DoFVecEnv(64, action_mode="setpoint", dtype=torch.float64, device=DEV, maxSteps=200, auto_reset=False, seed=2)
+    ob = env.reset()
+    d0 = torch.linalg.norm(env.path[:, 1] - env.systemState[:, :2], dim=1)
+    for _ in range(200):
+        a, _ = nav.predict(ob)
+        ob, _, _, _ = env.step(a)
+    d1 = torch.linalg.norm(env.path[:, 1] - env.systemState[:, :2], dim=1)
+    assert (d1 < 0.5 * d0).float().mean() > 0.9

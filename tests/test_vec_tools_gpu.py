@@ -1,0 +1,139 @@
+"""GPU: the callers / data formats either side of the step path: trajectory recorder
+and episode CSVs, evaluate_agent, the SB3 VecEnv adapter with VecMonitor CSV, the symmetry replay buffer."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from marinevehiclereinforcementlearning_b200 import AuvVecEnv, BlueROV2Heavy6DoFVecEnv, resources, vec_tools
+    from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence import flowGenerator, verySimpleAuv
+
+DEV = "cuda"
+
+
+def make_flow(g, dtype):
+    base = g["ltm"][None] + 0.05 * np.random.default_rng(7).standard_normal((int(g["nt"]),) + g["ltm"].shape)
+    return flowGenerator.ReconstructedFlow.from_base_field(base, float(g["base_dx"]), float(g["base_dy"]), float(g["base_dt"]), dtype=dtype, device=DEV)
+
+
+def test_recorder_reproduces_reference_time_history(tmp_path):
+    """6DoF: the recorder's 33-column rows for env 0 equal the reference env's timeHistory (golden)."""
+    e6 = load_golden("env6")
+    env = BlueROV2Heavy6DoFVecEnv(3, action_mode="setpoint", dtype=torch.float64, device=DEV, maxSteps=60, auto_reset=False, record_aux=True)
+    rec = vec_tools.TrajectoryRecorder(env, num_record=2)
+    env.reset(initialSetpoint=e6["fixed_sp"])
+    rec.on_reset()
+    for k in range(60):
+        env.step(torch.zeros((3, 6), dtype=torch.float64, device=DEV))
+        rec.on_step()
+    df = rec.dataframe(0)
+    assert list(df.columns) == list(e6["fixed_history_cols"]) and df.shape == (61, 33)
+    ref = e6["fixed_history"]
+    assert np.abs(df.values[:, :13] - ref[:, :13]).max() < 1e-8 and np.abs(df.values[:, 27:] - ref[:, 27:]).max() < 1e-12
+    assert np.abs(df.values[1:, 13:19] - ref[1:, 13:19]).max() < 1e-5
+    paths = rec.to_csv(str(tmp_path / "eval"))
+    assert [os.path.basename(p) for p in paths] == ["ep_0.csv", "ep_1.csv"]
+    back = np.loadtxt(paths[1], delimiter=",", skiprows=1)
+    assert back.shape == (61, 33) and np.abs(back - rec.dataframe(1).values).max() < 1e-12
+
+
+def test_recorder_legacy_columns_and_evaluate_agent(tmp_path):
+    g = load_golden("legacy")
+    flow = make_flow(g, torch.float64)
+    flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    e = 3
+    env = AuvVecEnv(2, flow, dtype=torch.float64, maxSteps=250, auto_reset=False, record_aux=True)
+    env.reset(applyNoise=False, fixedInitialValues=[g["ep_pos0"][e], float(g["ep_heading0"][e]), float(g["ep_heading_target"][e])])
+    env._target[1, :] = float(g["ep_t_offset"][e])
+    rec = vec_tools.TrajectoryRecorder(env, num_record=1)
+    rec.on_reset()
+    for k in range(20):
+        a = torch.as_tensor(np.repeat(g["ep_actions"][e, k:k + 1], 2, axis=0), device=DEV)
+        env.step(a)
+        rec.on_step(a)
+    df = rec.dataframe(0)
+    assert list(df.columns) == verySimpleAuv.HISTORY_COLUMNS and df.shape == (20, 40)
+    ref = g["ep_history"][e, :20]
+    scale = np.abs(ref) + np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(df.values - ref) / scale).max() < 1e-8
+    # evaluate_agent with the reference-shaped single env + PD controller (tag_00.../verySimpleAuv.py:437-447)
+    single = verySimpleAuv.AuvEnv(flow=make_flow(g, torch.float64))
+    single._max_episode_steps = 30
+    pd = verySimpleAuv.PDController(single.dt)
+    mean, median, rewards = resources.evaluate_agent(pd, single, num_episodes=2, saveDir=str(tmp_path / "pd"),
+                                                     init=[np.array([0.3, -0.2]), 1.0, 4.0])
+    assert len(rewards) == 2 and np.isfinite(mean) and os.path.exists(str(tmp_path / "pd" / "ep_1.csv"))
+    with open(str(tmp_path / "pd" / "ep_0.csv")) as fh:
+        assert next(csv.reader(fh)) == verySimpleAuv.HISTORY_COLUMNS
+    # batched: every environment runs the episode at once
+    benv = AuvVecEnv(64, flow, dtype=torch.float64, maxSteps=30, auto_reset=False)
+    mean_b, _, rewards_b = resources.evaluate_agent(verySimpleAuv.PDController(benv.dt), benv, num_episodes=1)
+    assert len(rewards_b) == 64 and np.isfinite(mean_b)
+
+
+def test_sb3_vecenv_protocol_and_monitor_csv(tmp_path):
+    env = BlueROV2Heavy6DoFVecEnv(16, action_mode="setpoint", dtype=torch.float32, device=DEV, maxSteps=4, auto_reset=True, seed=1)
+    venv = vec_tools.Sb3VecEnv(env, monitor_file=str(tmp_path / "run" / "agent_0"))
+    assert venv.num_envs == 16 and venv.observation_space.shape == (9,) and venv.action_space.shape == (6,)
+    obs = venv.reset()
+    assert obs.shape == (16, 9) and obs.dtype == np.float32
+    n_ep = 0
+    for k in range(9):
+        venv.step_async(np.random.default_rng(k).uniform(-1, 1, (16, 6)).astype(np.float32))
+        obs, rew, done, infos = venv.step_wait()
+        assert obs.shape == (16, 9) and rew.shape == (16,) and done.dtype == np.bool_ and len(infos) == 16
+        if (k + 1) % 4 == 0:
+            assert done.all()
+            assert all(i["episode"]["l"] == 4 and i["episode"]["r"] == 0.0 and i["terminal_observation"].shape == (9,) for i in infos)
+            assert all(i["TimeLimit.truncated"] for i in infos)
+            n_ep += 16
+        else:
+            assert not done.any() and all(i == {} for i in infos)
+    venv.close()
+    lines = open(str(tmp_path / "run" / "agent_0.monitor.csv")).read().splitlines()
+    assert lines[0].startswith("#{") and lines[1] == "r,l,t" and len(lines) == 2 + n_ep
+    assert venv.env_is_wrapped(object) == [False] * 16 and venv.get_attr("num_envs") == [16] * 16
+
+
+def test_symmetry_replay_buffer_matches_upstream_semantics():
+    """Against a numpy restatement of CustomReplayBuffer.add (main_02_sbl_contrib_customBuffer.py:57-160)."""
+    T_OBS = np.array([[1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], [-1, -1, 1, 1, -1, -1, -1, -1, 1, 1, 1], [-1, 1, 1, 1, -1, 1, -1, 1, 1, 1, 1],
+                      [1, -1, 1, 1, 1, -1, 1, -1, 1, 1, 1], [1, 1, -1, 1, 1, 1, 1, 1, -1, 1, 1]], dtype=np.float32)
+    T_ACT = np.array([[1, 1, 1], [-1, -1, 1], [-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=np.float32)
+    n, size = 37, 23
+    ref = {"o": np.zeros((size, n, 11), np.float32), "n": np.zeros((size, n, 11), np.float32), "a": np.zeros((size, n, 3), np.float32),
+           "r": np.zeros((size, n), np.float32), "d": np.zeros((size, n), np.uint8), "pos": 0, "full": False, "roll": 0}
+
+    def ref_add(o, no, a, r, d):
+        for i in range(5):
+            if ref["roll"] > 2 and i != 0:
+                continue
+            p = ref["pos"]
+            ref["o"][p], ref["n"][p], ref["a"][p], ref["r"][p], ref["d"][p] = o * T_OBS[i], no * T_OBS[i], a * T_ACT[i], r, d
+            ref["pos"] += 1
+            if ref["pos"] == size:
+                ref["full"], ref["pos"] = True, 0
+                ref["roll"] += 1
+
+    buf = vec_tools.SymmetryReplayBuffer(size, n, dtype=torch.float32, device=DEV)
+    rng = np.random.default_rng(0)
+    ld = 64
+    for k in range(30):
+        o, no, a = rng.uniform(-1, 1, (n, 11)).astype(np.float32), rng.uniform(-1, 1, (n, 11)).astype(np.float32), rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        r, d = rng.uniform(-3, 3, n).astype(np.float32), (rng.uniform(size=n) < 0.1).astype(np.uint8)
+        ref_add(o, no, a, r, d)
+        fm = lambda x, kdim: torch.as_tensor(np.pad(x.T, ((0, 0), (0, ld - n))), device=DEV).contiguous()
+        buf.add(fm(o, 11), fm(no, 11), fm(a, 3), torch.as_tensor(np.pad(r, (0, ld - n)), device=DEV), torch.as_tensor(np.pad(d, (0, ld - n)), device=DEV))
+        assert (buf.pos, buf.full, buf.nRollovers) == (ref["pos"], ref["full"], ref["roll"])
+    assert buf.nRollovers > 2   # both regimes (with and without mirror images) were exercised
+    for key, t in (("o", buf.observations), ("n", buf.next_observations), ("a", buf.actions), ("r", buf.rewards), ("d", buf.dones)):
+        assert np.array_equal(t.cpu().numpy(), ref[key]), key
+    s = buf.sample(256)
+    assert s["observations"].shape == (256, 11) and s["actions"].shape == (256, 3) and s["dones"].dtype == torch.uint8
