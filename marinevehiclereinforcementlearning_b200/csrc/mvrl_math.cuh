@@ -94,8 +94,9 @@ __device__ __forceinline__ F2 vcopysign(F2 mag, F2 sign) { return F2(copysignf(m
 // Python's float `%` (== numpy.mod): result takes the divisor's sign, and an
 // exact zero remainder is +0 for a positive divisor.  The reference wraps
 // angles with it (dynamicsModel_BlueROV2_Heavy_6DoF.py:560, resources.py:92-93).
-// |a| < b (the overwhelmingly common case for wrapped angles): no fmod, no branch.
-template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) { return a < T(0) ? a + b : tabs(a); }
+// -b < a < 2b (the overwhelmingly common case: an angle wrapped one step ago, moved by less than a turn):
+// no fmod, no branch.  a - b is exact for b <= a < 2b (Sterbenz), which is what fmod returns there.
+template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) { return a < T(0) ? a + b : (a >= b ? a - b : tabs(a)); }
 // general case, kept out of line: libm's fmod carries a long slow path that would otherwise be
 // inlined at every call site of the step kernels (measured: instruction-fetch stalls in the epilogue)
 template <typename T> __device__ __noinline__ T pymod_general(T a, T b) {
@@ -105,14 +106,14 @@ template <typename T> __device__ __noinline__ T pymod_general(T a, T b) {
     return r;
 }
 template <typename T> __device__ __forceinline__ T pymod_pos(T a, T b) {  // b > 0
-    if (tabs(a) < b) return pymod_small(a, b);
+    if (a > -b && a < b + b) return pymod_small(a, b);
     return pymod_general(a, b);
 }
 
 // resources.angleError (resources.py:75-95): a = (psi_d - psi) % 2pi, b = (psi - psi_d) % 2pi, a if a < b else -b
 template <typename T> __device__ __forceinline__ T angle_error_small(T d) {   // d = psi_d - psi, |d| < 2 pi
     const T tp = T(MVRL_TWO_PI);
-    const T a = pymod_small(d, tp), b = pymod_small(-d, tp);
+    const T a = d < T(0) ? d + tp : tabs(d), b = d > T(0) ? tp - d : tabs(d);   // d % 2pi and (-d) % 2pi for |d| < 2pi
     return a < b ? a : -b;
 }
 template <typename T> __device__ __forceinline__ T angle_error(T psi_d, T psi) {

@@ -32,17 +32,17 @@ __device__ __forceinline__ void observe6(const Rov6Dev<T>& P, const T (&y)[12], 
 }
 
 // 6DoF.py:560 + 467-483 on the fast path: wraps the three angles and fills the observation assuming every
-// angle and every angle error is inside (-2 pi, 2 pi); returns false when that does not hold (the caller
-// then redoes the angle part with the exact, out-of-line functions).  One compare at the end instead
-// of a branch per modulo.
+// angle is inside (-2 pi, 4 pi) and every angle error inside (-2 pi, 2 pi); returns false when that does not
+// hold (the caller then redoes the angle part with the exact, out-of-line functions).  One test at the end
+// instead of a branch per modulo.
 template <typename T>
 __device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T (&y)[12], const T (&path)[6], const T (&sp_ang)[3],
                                                    T (&wrapped)[3], T (&obs)[9]) {
     const T tp = T(MVRL_TWO_PI);
-    T worst = T(0);
+    T lo = y[3], hi = y[3], worst = T(0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        worst = tmax(worst, tabs(y[3 + k]));
+        lo = tmin(lo, y[3 + k]); hi = tmax(hi, y[3 + k]);
         wrapped[k] = pymod_small(y[3 + k], tp);
         const T d = sp_ang[k] - wrapped[k];
         worst = tmax(worst, tabs(d));
@@ -50,7 +50,7 @@ __device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T 
         obs[3 + k] = clampt((path[3 + k] - y[k]) * P.inv_3L, T(-1), T(1));
         obs[6 + k] = clampt(angle_error_small(d) * P.inv_ang, T(-1), T(1));
     }
-    return worst < tp;
+    return lo > -tp && hi < tp + tp && worst < tp;   // all false for NaN: the exact path then propagates it
 }
 
 // the exact angle part (any magnitude), out of line: wrapped angle and clipped, scaled angle error
@@ -114,6 +114,23 @@ __device__ __forceinline__ void stats_accumulate(double* stats, bool is_done, do
         }
     }
     if (bm && lane == leader) atomicAdd(stats + 5, (double)__popc(bm));
+}
+
+// Zero-reward envs (3DoF / 6DoF), counts only: one vote + three hardware warp reductions (REDUX) per thread,
+// atomics from one lane of the warps that actually saw a terminal / non-finite environment.
+__device__ __forceinline__ void stats_accumulate_counts(double* stats, int n_done, int len_sum, int n_bad) {
+    const unsigned active = __activemask();
+    if (!__any_sync(active, (n_done | n_bad) != 0)) return;
+    const int d = __reduce_add_sync(active, n_done), l = __reduce_add_sync(active, len_sum), b = __reduce_add_sync(active, n_bad);
+    if ((int)(threadIdx.x & 31) == __ffs(active) - 1) {
+        if (d) {
+            atomicAdd(stats + 0, (double)d);
+            atomicAdd(stats + 1, (double)l);
+            stats[3] = 0.0;   // min / max return: every writer stores the same constant
+            stats[4] = 0.0;
+        }
+        if (b) atomicAdd(stats + 5, (double)b);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -303,6 +320,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) sp_v[k] = V(T(0));
     }
+    int n_done_t = 0, len_t = 0, n_bad_t = 0;
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         if (l == 1 && !pair) break;
@@ -348,7 +366,8 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                 for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, T(lane_get(dem[k], l)));
             }
         }
-        if (a.stats != nullptr) stats_accumulate<false>(a.stats, is_done && a.auto_reset, (double)istep, 0.0, bad);
+        if (is_done && a.auto_reset) { n_done_t += 1; len_t += istep; }
+        n_bad_t += bad ? 1 : 0;
 
         int istep_out = istep;
         T eo[6], ei[6];
@@ -400,6 +419,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         }
     }
 
+    if (a.stats != nullptr) stats_accumulate_counts(a.stats, n_done_t, len_t, n_bad_t);
 #pragma unroll
     for (int k = 0; k < 12; ++k) store_v<V>(a.state + k * ld, i0, pair, y[k]);
 #pragma unroll
