@@ -133,6 +133,49 @@ __device__ __forceinline__ void stats_accumulate_counts(double* stats, int n_don
     }
 }
 
+// Auto-reset of ONE terminated environment (SB3 VecEnv convention; reset semantics of 6DoF.py:485-529), run by
+// the step kernel after its regular stores: keeps the terminal observation, bumps the episode counter, zeroes
+// the state, draws the next path / target orientation (unless the set-point is fixed), installs a fresh
+// controller and writes the observation of the fresh state.  Out of line: one environment in max_steps takes it.
+template <typename T, int MODE>
+__device__ __noinline__ void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long i) {
+    const long ld = a.ld;
+    const Rov6Dev<T>& P = a.P;
+    if (a.term_obs != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = a.obs[k * ld + i];
+    }
+    const uint32_t ep = a.episode[i] + 1u;
+    a.episode[i] = ep;
+    a.istep[i] = 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) a.state[k * ld + i] = T(0);
+    T path[6], ang[3];
+    if (!a.fixed_sp) {
+        const Reset6<T> rs = draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { path[k] = rs.path[k]; a.path[k * ld + i] = path[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ang[k] = rs.orient[k]; a.setpoint[k * ld + i] = path[k]; a.setpoint[(3 + k) * ld + i] = ang[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) path[k] = a.path[k * ld + i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ang[k] = a.setpoint[(3 + k) * ld + i];
+    }
+    if constexpr (MODE == ACT_SETPOINT) {  // fresh controller, 6DoF.py:37-41, 514
+#pragma unroll
+        for (int k = 0; k < 13; ++k) a.ctrl[k * ld + i] = T(0);
+        a.ctrl[i] = Real<T>::nan();
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // dataToState of the zero state
+        a.obs[k * ld + i] = clampt(path[k] * P.inv_3L, T(-1), T(1));
+        a.obs[(3 + k) * ld + i] = clampt(path[3 + k] * P.inv_3L, T(-1), T(1));
+        a.obs[(6 + k) * ld + i] = wrap_angle_exact(P.inv_ang, T(0), ang[k]).obs;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K1: fused env step.  action -> (set-point) -> n_sub x RK4 in registers ->
 // wrap -> observation -> done -> reward -> auto-reset.
@@ -309,20 +352,18 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         }
     }
 
-    // ---- epilogue, per environment (scalar): wrap, observe, done, stats, auto-reset ----
+    // ---- epilogue: wrap, observe, done, stats - straight-line for every environment of the thread; the
+    // auto-reset of a terminated environment is an out-of-line fix-up AFTER the regular stores (it overwrites
+    // that environment's rows; same thread, so program order makes the later stores win) ----
     V nonfinite = V(T(0));   // sum of 0 * y_k: 0 when every state is finite, NaN otherwise
 #pragma unroll
     for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
-    V obs_v[9], sp_v[6], eo_v[6], ei_v[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { sp_v[k] = sp[k]; eo_v[k] = e_old[k]; ei_v[k] = e_int[k]; }
-    if constexpr (MODE != ACT_SETPOINT) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sp_v[k] = V(T(0));
-    }
+    V obs_v[9];
     int n_done_t = 0, len_t = 0, n_bad_t = 0;
+    bool reset_lane[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
+        reset_lane[l] = false;
         if (l == 1 && !pair) break;
         const long i = i0 + l;
         T ys[12];
@@ -336,10 +377,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         T path[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
-        T sps[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) sps[k] = lane_get(sp_v[k], l);
-        const T spa[3] = {sps[3], sps[4], sps[5]};
+        const T spa[3] = {lane_get(sp[3], l), lane_get(sp[4], l), lane_get(sp[5], l)};
         T obs[9], wrapped[3];
         // 6DoF.py:560 (wrap) and 467-483 (dataToState)
         if (!wrap_observe6_fast(P, ys, path, spa, wrapped, obs)) {
@@ -350,7 +388,9 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) ys[3 + k] = wrapped[k];
+        for (int k = 0; k < 3; ++k) lane_set(y[3 + k], l, wrapped[k]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) lane_set(obs_v[k], l, obs[k]);
         const bool is_done = istep >= a.max_steps;  // 6DoF.py:569-571
 
         if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
@@ -366,57 +406,12 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                 for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, T(lane_get(dem[k], l)));
             }
         }
-        if (is_done && a.auto_reset) { n_done_t += 1; len_t += istep; }
+        reset_lane[l] = is_done && a.auto_reset;
+        if (reset_lane[l]) { n_done_t += 1; len_t += istep; }
         n_bad_t += bad ? 1 : 0;
-
-        int istep_out = istep;
-        T eo[6], ei[6];
-        if constexpr (MODE == ACT_SETPOINT) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { eo[k] = lane_get(eo_v[k], l); ei[k] = lane_get(ei_v[k], l); }
-        }
-        if (is_done && a.auto_reset) {
-            if (a.term_obs != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = obs[k];
-            }
-            const uint32_t ep = a.episode[i] + 1u;
-            a.episode[i] = ep;
-            istep_out = 0;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) ys[k] = T(0);
-            if (!a.fixed_sp) {
-                const Reset6<T> rs = draw_reset6<T>(a.seed, a.env_id0 + (unsigned long long)i, ep);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { path[k] = rs.path[k]; a.path[k * ld + i] = path[k]; }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { sps[k] = path[k]; sps[3 + k] = rs.orient[k]; }
-#pragma unroll
-                for (int k = 0; k < 6; ++k) a.setpoint[k * ld + i] = sps[k];
-            }
-            if constexpr (MODE == ACT_SETPOINT) {  // fresh controller, 6DoF.py:37-41, 514
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { eo[k] = T(0); ei[k] = T(0); }
-                eo[0] = Real<T>::nan();
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                obs[k] = clampt(path[k] * P.inv_3L, T(-1), T(1));        // the fresh state is zero
-                obs[3 + k] = clampt(path[3 + k] * P.inv_3L, T(-1), T(1));
-                obs[6 + k] = wrap_angle_exact(P.inv_ang, T(0), sps[3 + k]).obs;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) lane_set(y[k], l, ys[k]);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) lane_set(obs_v[k], l, obs[k]);
         a.done[i] = is_done ? 1 : 0;
-        a.istep[i] = istep_out;
-        if constexpr (MODE == ACT_SETPOINT) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { lane_set(sp_v[k], l, sps[k]); lane_set(eo_v[k], l, eo[k]); lane_set(ei_v[k], l, ei[k]); }
-            a.ctrl[12 * ld + i] = T(istep_out) * a.dt;
-        }
+        a.istep[i] = istep;
+        if constexpr (MODE == ACT_SETPOINT) a.ctrl[12 * ld + i] = T(istep) * a.dt;
     }
 
     if (a.stats != nullptr) stats_accumulate_counts(a.stats, n_done_t, len_t, n_bad_t);
@@ -428,10 +423,14 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     if constexpr (MODE == ACT_SETPOINT) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            store_v<V>(a.setpoint + k * ld, i0, pair, sp_v[k]);
-            store_v<V>(a.ctrl + k * ld, i0, pair, eo_v[k]);
-            store_v<V>(a.ctrl + (6 + k) * ld, i0, pair, ei_v[k]);
+            store_v<V>(a.setpoint + k * ld, i0, pair, sp[k]);
+            store_v<V>(a.ctrl + k * ld, i0, pair, e_old[k]);
+            store_v<V>(a.ctrl + (6 + k) * ld, i0, pair, e_int[k]);
         }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        if (reset_lane[l]) rov6_auto_reset_env<T, MODE>(a, i0 + l);
     }
 }
 
