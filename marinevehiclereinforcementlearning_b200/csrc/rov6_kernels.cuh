@@ -360,40 +360,63 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
     V obs_v[9];
     int n_done_t = 0, len_t = 0, n_bad_t = 0;
-    bool reset_lane[L];
+    bool reset_lane[L], lane_on[L], ok[L];
+    int istep[L];
+    T ang_raw[L][3], spa[L][3];
+    // phase A - both environments of the thread in one basic block (no branch in between: the two dependency
+    // chains interleave): wrap (6DoF.py:560) and dataToState (467-483) on the fast path
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-        reset_lane[l] = false;
-        if (l == 1 && !pair) break;
-        const long i = i0 + l;
-        T ys[12];
+        lane_on[l] = (l == 0) || pair;
+        T ys[12], path[6], obs[9], wrapped[3];
 #pragma unroll
         for (int k = 0; k < 12; ++k) ys[k] = lane_get(y[k], l);
-        const int istep = istep_in[l] + 1;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { spa[l][k] = lane_get(sp[3 + k], l); ang_raw[l][k] = ys[3 + k]; }
+        istep[l] = istep_in[l] + 1;
         bool bad = lane_get(nonfinite, l) != T(0);   // NaN compares unequal
         if constexpr (sizeof(T) == 4 && !FAST) {  // outside the exact range of the fp32 sin/cos reduction
             bad = bad || tmax(tmax(tabs(ys[3]), tabs(ys[4])), tabs(ys[5])) > T(MVRL_SINCOS_F32_MAX_ARG);
         }
-        T path[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
-        const T spa[3] = {lane_get(sp[3], l), lane_get(sp[4], l), lane_get(sp[5], l)};
-        T obs[9], wrapped[3];
-        // 6DoF.py:560 (wrap) and 467-483 (dataToState)
-        if (!wrap_observe6_fast(P, ys, path, spa, wrapped, obs)) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const WrapObs<T> r = wrap_angle_exact(P.inv_ang, ys[3 + k], spa[k]);
-                wrapped[k] = r.wrapped; obs[6 + k] = r.obs;
-            }
-        }
+        ok[l] = wrap_observe6_fast(P, ys, path, spa[l], wrapped, obs) || !lane_on[l];
 #pragma unroll
         for (int k = 0; k < 3; ++k) lane_set(y[3 + k], l, wrapped[k]);
 #pragma unroll
         for (int k = 0; k < 9; ++k) lane_set(obs_v[k], l, obs[k]);
-        const bool is_done = istep >= a.max_steps;  // 6DoF.py:569-571
-
-        if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
+        const bool is_done = istep[l] >= a.max_steps;  // 6DoF.py:569-571
+        reset_lane[l] = lane_on[l] && is_done && a.auto_reset;
+        n_done_t += reset_lane[l] ? 1 : 0;
+        len_t += reset_lane[l] ? istep[l] : 0;
+        n_bad_t += (lane_on[l] && bad) ? 1 : 0;
+        if (lane_on[l]) {
+            a.done[i0 + l] = is_done ? 1 : 0;
+            a.istep[i0 + l] = istep[l];
+            if constexpr (MODE == ACT_SETPOINT) a.ctrl[12 * ld + i0 + l] = T(istep[l]) * a.dt;
+        }
+    }
+    // phase B - rare: an angle outside the fast range goes through the exact, out-of-line modulo
+    bool all_ok = true;
+#pragma unroll
+    for (int l = 0; l < L; ++l) all_ok = all_ok && ok[l];
+    if (!all_ok) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            if (ok[l]) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const WrapObs<T> r = wrap_angle_exact(P.inv_ang, ang_raw[l][k], spa[l][k]);
+                lane_set(y[3 + k], l, r.wrapped);
+                lane_set(obs_v[6 + k], l, r.obs);
+            }
+        }
+    }
+    if (a.aux != nullptr) {  // what the reference logs per step, 6DoF.py:578-580
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            if (!lane_on[l]) continue;
+            const long i = i0 + l;
             if constexpr (MODE == ACT_RPM) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) a.aux[k * ld + i] = T(0);
@@ -406,12 +429,6 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                 for (int k = 0; k < 8; ++k) a.aux[(6 + k) * ld + i] = demand_to_rpm(P, T(lane_get(dem[k], l)));
             }
         }
-        reset_lane[l] = is_done && a.auto_reset;
-        if (reset_lane[l]) { n_done_t += 1; len_t += istep; }
-        n_bad_t += bad ? 1 : 0;
-        a.done[i] = is_done ? 1 : 0;
-        a.istep[i] = istep;
-        if constexpr (MODE == ACT_SETPOINT) a.ctrl[12 * ld + i] = T(istep) * a.dt;
     }
 
     if (a.stats != nullptr) stats_accumulate_counts(a.stats, n_done_t, len_t, n_bad_t);
