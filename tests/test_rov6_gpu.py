@@ -302,7 +302,11 @@ def test_step_host_and_step_range_match_step_bitwise():
         a.reset(); b.reset(); c.reset()
         for k in range(steps):
             obs, rew, done, _ = a.step(acts[k].to(DEV))
-            h_obs, h_rew, h_done = b.step_host(acts[k].pin_memory(), chunks=3 if k % 2 else -3)  # CUDA-graph replay / direct streams
+            if k % 3 == 2:   # pageable host memory: copy-engine path with device staging
+                outs = (torch.empty((n, 9), dtype=dtype), torch.empty(n, dtype=dtype), torch.empty(n, dtype=torch.uint8))
+                h_obs, h_rew, h_done = b.step_host(acts[k].clone(), *outs, chunks=3)
+            else:            # pinned: overlapping copies; CUDA-graph replay / direct streams
+                h_obs, h_rew, h_done = b.step_host(acts[k].pin_memory(), chunks=3 if k % 2 else -3)
             c.set_actions(acts[k].to(DEV))
             for first in range(0, n, 1111):
                 c.step_range_async(first, min(1111, n - first))
