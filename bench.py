@@ -457,20 +457,27 @@ def run_rollout(args, rank, local_rank, world):
     buf_rew = torch.empty((T, ld), device=dev)
     buf_done = torch.empty((T, ld), dtype=torch.uint8, device=dev)
 
-    def policy(x):            # feature-major: x [9, N] -> mean [6, N]; W x needs no transposes of the SoA buffers
+    Wt = [w.T.contiguous() for w in Ws]         # [in, out]
+    b1 = [b.reshape(-1).contiguous() for b in bs]
+    obs_nk = env._obs.T                          # [ld, 9] strided view of the SoA observation buffer: cuBLAS reads it in place
+
+    def policy(x_nk):         # batch-major activations [N, k]; bias + GELU fused into the GEMM epilogue (cuBLASLt)
+        h = x_nk
         for i in range(3):
-            x = torch.nn.functional.gelu(torch.addmm(bs[i], Ws[i], x))
-        return torch.tanh(torch.addmm(bs[3], Ws[3], x))
+            h = torch._addmm_activation(b1[i], h, Wt[i], use_gelu=True)
+        return torch.tanh(torch.addmm(b1[3], h, Wt[3]))      # [N, 6]
+
+    std = log_std.exp().reshape(1, 6)
+    logp_const = float(-log_std.sum())
 
     def rollout():
         for t in range(T):
-            obs = env._obs
-            buf_obs[t].copy_(obs)
-            mean = policy(obs)
+            buf_obs[t].copy_(env._obs)
+            mean = policy(obs_nk)
             eps = torch.randn_like(mean)
-            act = (mean + eps * log_std.exp()).clamp_(-1., 1.)
-            buf_logp[t].copy_((-0.5 * eps * eps - log_std).sum(0))
-            buf_act[t].copy_(act)
+            act = torch.addcmul(mean, eps, std).clamp_(-1., 1.)
+            buf_logp[t].copy_((eps * eps).sum(1).mul_(-0.5).add_(logp_const))
+            buf_act[t].copy_(act.T)             # back to the env's feature-major action layout
             env._bufs.action = buf_act[t].data_ptr()
             env.step_async()
             buf_rew[t].copy_(env._reward)

@@ -258,10 +258,15 @@ MVRL_API int mvrl_los_navigation(int dtype, int64_t n, int64_t ld, const void* o
 /* -------------------------------------------------------------- legacy -- */
 
 /* AuvEnv constants, tag_00.../verySimpleAuv.py:110-132 */
+#define MVRL_AUV_PLAIN 0   /* AuvEnv: target at the origin, V3 observation */
+#define MVRL_AUV_CYL 1     /* AuvEnvCyl (verySimpleAuv_cyl.py:22-345): way-point list, V0 observation scaling */
 typedef struct MvrlAuvParams {
     double m, Izz, Xuu, Yvv, Nrr, Xu, Yv, Nr, maxForce, maxMoment;
     double xMin, xMax, yMin, yMax;
     double noiseMagCoeffs, noiseMagActuation;
+    double wp_threshold;          /* AuvEnvCyl: a way-point counts as reached inside this radius (Rcyl * 0.05) */
+    double waypoints[32 * 3];     /* AuvEnvCyl: x, y, target heading per way-point (verySimpleAuv_cyl.py:33-39) */
+    int variant, n_waypoints;
 } MvrlAuvParams;
 
 typedef struct MvrlAuvConfig {
@@ -283,6 +288,7 @@ typedef struct MvrlAuvBuffers {
     void* err_o;        /* T [3][ld] perr_o x, perr_o y, herr_o                     in/out */
     void* recent;       /* T [30][ld] the 10 most recent actions (ring)             in/out */
     void* ep_return;    /* T [ld] running episode return                            in/out */
+    int32_t* iwp;       /* [ld] way-point index, AuvEnvCyl only (never reset, as upstream)  in/out; nullable for AuvEnv */
     uint32_t* episode;  /* [ld] */
     void* terminal_obs; /* T [11][ld], nullable */
     void* aux;          /* T [14][ld] Fx Fy N Fx_set Fy_set N_set u_current v_current rmsAc r0..r4

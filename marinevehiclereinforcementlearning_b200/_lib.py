@@ -64,9 +64,13 @@ MvrlRov3Config = MvrlRov6Config
 MvrlRov3Buffers = MvrlRov6Buffers  # same members, different leading dimensions per array
 
 
+AUV_PLAIN, AUV_CYL = 0, 1
+
+
 class MvrlAuvParams(C.Structure):
     _fields_ = [(n, _d) for n in ("m", "Izz", "Xuu", "Yvv", "Nrr", "Xu", "Yv", "Nr", "maxForce", "maxMoment",
-                                  "xMin", "xMax", "yMin", "yMax", "noiseMagCoeffs", "noiseMagActuation")]
+                                  "xMin", "xMax", "yMin", "yMax", "noiseMagCoeffs", "noiseMagActuation", "wp_threshold")] + \
+        [("waypoints", _d * 96), ("variant", C.c_int), ("n_waypoints", C.c_int)]
 
 
 class MvrlAuvConfig(C.Structure):
@@ -76,7 +80,7 @@ class MvrlAuvConfig(C.Structure):
 
 class MvrlAuvBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state", "action", "obs", "reward", "done", "istep", "mults", "target", "err_o",
-                                          "recent", "ep_return", "episode", "terminal_obs", "aux", "ep_stats")]
+                                          "recent", "ep_return", "iwp", "episode", "terminal_obs", "aux", "ep_stats")]
 
 
 _vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int

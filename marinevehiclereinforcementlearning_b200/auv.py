@@ -125,6 +125,8 @@ class AuvVecEnv:
     termination and SB3-style auto-reset.  Tensors stay on the device; ``obs``
     / ``actions`` are ``[N, k]`` views of feature-major ``[k, ld]`` buffers."""
     STATE_DIM, OBS_DIM, ACT_DIM = 6, 11, 3
+    VARIANT = _lib.AUV_PLAIN
+    BOUNDS = 1.
 
     def __init__(self, num_envs, flow, seed=0, dt=0.02, maxSteps=250, noiseMagCoeffs=0.0, noiseMagActuation=0.0,
                  stopOnBoundsExceeded=True, applyNoise=True, dtype=torch.float32, device=None, auto_reset=True,
@@ -138,7 +140,8 @@ class AuvVecEnv:
         self.seed, self.env_id0, self.auto_reset = int(seed), int(env_id0), bool(auto_reset)
         self.stopOnBoundsExceeded, self.applyNoise = bool(stopOnBoundsExceeded), bool(applyNoise)
         # verySimpleAuv.py:110-132
-        self.xMinMax, self.yMinMax = [-1., 1.], [-1., 1.]
+        self.xMinMax, self.yMinMax = [-self.BOUNDS, self.BOUNDS], [-self.BOUNDS, self.BOUNDS]
+        self.waypoints, self.wpThreshold = np.zeros((0, 3)), 0.
         self.m, self.Izz = 11.4, 0.16
         self.Xuu, self.Yvv, self.Nrr = -18.18 * 2.21, -21.66 * 4.87, -1.55
         self.Xu, self.Yv, self.Nr = -4.03 * 2.21, -6.22 * 4.87, -0.07
@@ -156,6 +159,7 @@ class AuvVecEnv:
         self._mults, self._target, self._err_o, self._recent = z(11), z(2), z(3), z(30)
         self._mults.fill_(1.)
         self._ep_return = torch.zeros(ld, dtype=dtype, device=dev)
+        self._iwp = torch.zeros(ld, dtype=torch.int32, device=dev)       # AuvEnvCyl only; never reset, as upstream
         self._episode = torch.zeros(ld, dtype=torch.int32, device=dev)
         self._terminal_obs = z(11) if (record_terminal_obs and auto_reset) else None
         self._aux = z(len(AUX_COLUMNS)) if record_aux else None
@@ -166,7 +170,7 @@ class AuvVecEnv:
             state=self._state.data_ptr(), action=self._action.data_ptr(), obs=self._obs.data_ptr(), reward=self._reward.data_ptr(),
             done=self._done.data_ptr(), istep=self._istep.data_ptr(), mults=self._mults.data_ptr(), target=self._target.data_ptr(),
             err_o=self._err_o.data_ptr(), recent=self._recent.data_ptr(), ep_return=self._ep_return.data_ptr(),
-            episode=self._episode.data_ptr(),
+            iwp=self._iwp.data_ptr(), episode=self._episode.data_ptr(),
             terminal_obs=None if self._terminal_obs is None else self._terminal_obs.data_ptr(),
             aux=None if self._aux is None else self._aux.data_ptr(),
             ep_stats=None if self._stats is None else self._stats.data_ptr())
@@ -184,12 +188,15 @@ class AuvVecEnv:
         key = (self.m, self.Izz, self.Xuu, self.Yvv, self.Nrr, self.Xu, self.Yv, self.Nr, self.maxForce, self.maxMoment,
                tuple(self.xMinMax), tuple(self.yMinMax), self.noiseMagCoeffs, self.noiseMagActuation, self.dt,
                self._max_episode_steps, self.seed, self.env_id0, self.auto_reset, self.stopOnBoundsExceeded, apply_noise,
-               f._uv.data_ptr(), f.dx, f.dy, f.dt)
+               f._uv.data_ptr(), f.dx, f.dy, f.dt, self.wpThreshold, np.asarray(self.waypoints, dtype=float).tobytes())
         if self._handle is None or key != self._handle_key:
             p = _lib.MvrlAuvParams(m=self.m, Izz=self.Izz, Xuu=self.Xuu, Yvv=self.Yvv, Nrr=self.Nrr, Xu=self.Xu, Yv=self.Yv, Nr=self.Nr,
                                    maxForce=self.maxForce, maxMoment=self.maxMoment, xMin=self.xMinMax[0], xMax=self.xMinMax[1],
                                    yMin=self.yMinMax[0], yMax=self.yMinMax[1], noiseMagCoeffs=self.noiseMagCoeffs,
-                                   noiseMagActuation=self.noiseMagActuation)
+                                   noiseMagActuation=self.noiseMagActuation, wp_threshold=float(self.wpThreshold),
+                                   variant=self.VARIANT, n_waypoints=len(self.waypoints))
+            flat = np.asarray(self.waypoints, dtype=float).reshape(-1)
+            p.waypoints[:len(flat)] = list(flat)
             cfg = _lib.MvrlAuvConfig(dtype=_lib.torch_dtype_code(self.dtype), max_steps=self._max_episode_steps, dt=self.dt,
                                      seed=self.seed & (2 ** 64 - 1), env_id0=self.env_id0, auto_reset=int(self.auto_reset),
                                      stop_on_bounds=int(self.stopOnBoundsExceeded), apply_noise=int(apply_noise), device=self.device.index)
@@ -300,7 +307,7 @@ class AuvVecEnv:
             self._reset_stats()
         return out
 
-    _STATE_KEYS = ("_state", "_istep", "_mults", "_target", "_err_o", "_recent", "_ep_return", "_episode", "_obs")
+    _STATE_KEYS = ("_state", "_istep", "_mults", "_target", "_err_o", "_recent", "_ep_return", "_iwp", "_episode", "_obs")
 
     def state_dict(self):
         return {k: getattr(self, k).clone() for k in self._STATE_KEYS}
@@ -309,3 +316,39 @@ class AuvVecEnv:
         for k, v in d.items():
             getattr(self, k).copy_(v)
         self._needs_episode_bump = True
+
+
+def cyl_waypoints(Rcyl=1.33, xCyl=(2.5, 0.)):
+    """verySimpleAuv_cyl.py:29-41: 21 way-points (x, y, target heading) on an arc around the cylinder and the
+    radius inside which a way-point counts as reached.  Host set-up, exactly the reference's numpy expressions."""
+    Rwp = Rcyl * 1.3
+    t = np.linspace(-30, 30, 21) * np.pi / 180.
+    return np.vstack([-Rwp * np.cos(t) + xCyl[0], Rwp * np.sin(t) + xCyl[1], -t]).T, Rcyl * 0.05
+
+
+class AuvCylVecEnv(AuvVecEnv):
+    """N legacy ``AuvEnvCyl`` environments (verySimpleAuv_cyl.py:22-345): the position / heading targets walk
+    along the way-point list, V0 observation scaling, bounds +-2, 1200-step episodes.  ``fixedInitialValues``
+    = (position, heading[, ignored]).  The way-point index of an environment survives resets, as upstream."""
+    VARIANT = _lib.AUV_CYL
+    BOUNDS = 2.
+
+    def __init__(self, num_envs, flow, maxSteps=1200, **kw):
+        super().__init__(num_envs, flow, maxSteps=maxSteps, **kw)
+        self.Rcyl, self.xCyl = 1.33, np.array([2.5, 0.])
+        self.waypoints, self.wpThreshold = cyl_waypoints(self.Rcyl, self.xCyl)
+
+    @property
+    def iWp(self):
+        return self._iwp[:self.num_envs]
+
+    @property
+    def positionTarget(self):
+        wp = torch.as_tensor(self.waypoints[:, :2], dtype=self.dtype, device=self.device)
+        return wp[self.iWp.long()]
+
+    def reset(self, applyNoise=None, fixedInitialValues=None, mask=None):
+        if fixedInitialValues is not None:
+            pos, heading = fixedInitialValues[0], fixedInitialValues[1]
+            fixedInitialValues = (pos, heading, 0.)
+        return super().reset(applyNoise=applyNoise, fixedInitialValues=fixedInitialValues, mask=mask)

@@ -94,6 +94,10 @@ template <typename T> struct AuvDev {
     T xmin, xmax, ymin, ymax;
     T noise_coeffs, noise_act;
     T t_quarter;  // flow.time[nt // 4], upper bound of the random flow time offset
+    // AuvEnvCyl (verySimpleAuv_cyl.py:29-41): way-points x, y, target heading; switch radius
+    int cyl, n_wp;
+    T wp_thr;
+    T wp[32][3];
 };
 
 template <typename T> struct AuvStepArgs {
@@ -109,6 +113,7 @@ template <typename T> struct AuvStepArgs {
     T* err_o;        // [3][ld] perr_o x, perr_o y, herr_o
     T* recent;       // [30][ld] ring of the 10 most recent actions (slot = (iStep - 1) % 10)
     T* ep_return;    // [ld] running episode return
+    int32_t* iwp;    // [ld] way-point index (AuvEnvCyl only)
     uint32_t* episode; T* term_obs; T* aux; double* stats;
     T dt;
     int max_steps;
@@ -116,20 +121,25 @@ template <typename T> struct AuvStepArgs {
     int auto_reset, stop_on_bounds, apply_noise;
 };
 
-// dataToState V3, verySimpleAuv.py:147-214
+// dataToState: V3 of AuvEnv (verySimpleAuv.py:147-214; target at the origin, no scaling) or, for AuvEnvCyl,
+// V0 scaling against the current way-point (verySimpleAuv_cyl.py:84-115)
 template <typename T>
-__device__ __forceinline__ void observe_auv(T x, T y, T psi, T u, T v, T r, T heading_target, T perr_ox, T perr_oy, T herr_o, T (&obs)[11]) {
-    const T px = -x, py = -y;  // positionTarget = 0
+__device__ __forceinline__ void observe_auv(bool cyl, T tx, T ty, T x, T y, T psi, T u, T v, T r, T heading_target, T perr_ox, T perr_oy,
+                                            T herr_o, T (&obs)[11]) {
+    const T px = tx - x, py = ty - y;
     const T herr = angle_error(heading_target, psi);
-    obs[0] = clampt(px, T(-1), T(1));
-    obs[1] = clampt(py, T(-1), T(1));
-    obs[2] = clampt(herr / T(45. / 180. * 3.14159265358979323846), T(-1), T(1));
-    obs[3] = clampt(herr - herr_o, T(-1), T(1));
-    obs[4] = clampt(px - perr_ox, T(-1), T(1));
-    obs[5] = clampt(py - perr_oy, T(-1), T(1));
-    obs[6] = clampt(u, T(-1), T(1));
-    obs[7] = clampt(v, T(-1), T(1));
-    obs[8] = clampt(r, T(-1), T(1));
+    const T pi = T(3.14159265358979323846);
+    const T sp = cyl ? T(0.2) : T(1), sdh = cyl ? T(2. / 180 * 3.14159265358979323846) : T(1), sdp = cyl ? T(0.025) : T(1);
+    const T sv = cyl ? T(0.2) : T(1), sr = cyl ? T(30. / 180. * 3.14159265358979323846) : T(1);
+    obs[0] = clampt(px / sp, T(-1), T(1));
+    obs[1] = clampt(py / sp, T(-1), T(1));
+    obs[2] = clampt(herr / (T(45. / 180.) * pi), T(-1), T(1));
+    obs[3] = clampt((herr - herr_o) / sdh, T(-1), T(1));
+    obs[4] = clampt((px - perr_ox) / sdp, T(-1), T(1));
+    obs[5] = clampt((py - perr_oy) / sdp, T(-1), T(1));
+    obs[6] = clampt(u / sv, T(-1), T(1));
+    obs[7] = clampt(v / sv, T(-1), T(1));
+    obs[8] = clampt(r / sr, T(-1), T(1));
     obs[9] = T(0);
     obs[10] = T(0);
 }
@@ -151,8 +161,12 @@ __device__ __forceinline__ void draw_reset_auv(const AuvDev<T>& P, unsigned long
     *x = (u01<T>(w[11]) - T(0.5)) * T(0.5) * (P.xmax - P.xmin);
     *y = (u01<T>(w[12]) - T(0.5)) * T(0.5) * (P.ymax - P.ymin);
     *heading = u01<T>(w[13]) * T(MVRL_TWO_PI);
-    *target = u01<T>(w[14]) * T(MVRL_TWO_PI);
-    *offset = u01<T>(w[15]) * P.t_quarter;
+    if (P.cyl) {   // verySimpleAuv_cyl.py:155-160: the heading target comes from the way-point, one draw fewer
+        *offset = u01<T>(w[14]) * P.t_quarter;
+    } else {
+        *target = u01<T>(w[14]) * T(MVRL_TWO_PI);
+        *offset = u01<T>(w[15]) * P.t_quarter;
+    }
 }
 
 // K4: AuvEnv.step, verySimpleAuv.py:264-410
@@ -167,6 +181,9 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     const long ld = a.ld;
     T x = a.state[i], y = a.state[ld + i], psi = a.state[2 * ld + i];
     T heading_target = a.target[i], t_offset = a.target[ld + i];
+    int iwp = 0;
+    T tx = T(0), ty = T(0);   // positionTarget: the origin, or the current way-point of AuvEnvCyl
+    if (P.cyl) { iwp = a.iwp[i]; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
     const int istep = a.istep[i] + 1;
     const T time = T(istep) * a.dt;
     const FlowCell<T> cell = flow_locate(a.flow, time + t_offset, x, y);
@@ -221,13 +238,17 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     r = r + ar * a.dt;
 
     T obs[11];
-    observe_auv(x, y, psi, u, v, r, heading_target, a.err_o[i], a.err_o[ld + i], a.err_o[2 * ld + i], obs);
+    observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, a.err_o[i], a.err_o[ld + i], a.err_o[2 * ld + i], obs);
 
     T bonus = T(0);
     if (x < P.xmin || x > P.xmax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
     if (y < P.ymin || y > P.ymax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
-    T perr_x = -x, perr_y = -y;
+    T perr_x = tx - x, perr_y = ty - y;
     T herr = angle_error(heading_target, psi);
+    if (P.cyl && Real<T>::sqrt(perr_x * perr_x + perr_y * perr_y) < P.wp_thr) {   // way-point reached (verySimpleAuv_cyl.py:249-253);
+        iwp = iwp + 1 < P.n_wp ? iwp + 1 : P.n_wp - 1;                            // the errors above stay relative to the OLD target
+        tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2];
+    }
 
     // rmsAc: mean over components of the population std of the <= 10 recent actions (:353-355)
     T rms = T(0);
@@ -272,15 +293,16 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
         draw_reset_auv(P, a.seed, a.env_id0 + (unsigned long long)i, ep, a.apply_noise != 0, mm, &x, &y, &psi, &heading_target, &t_offset);
 #pragma unroll
         for (int k = 0; k < 11; ++k) a.mults[k * ld + i] = mm[k];
-        a.target[i] = heading_target;
         a.target[ld + i] = t_offset;
         u = v = r = T(0);
         istep_out = 0;
         ep_ret_out = T(0);
-        perr_x = -x; perr_y = -y;
+        perr_x = tx - x; perr_y = ty - y;     // (the way-point index is NOT reset: upstream sets it in __init__ only)
         herr = angle_error(heading_target, psi);
-        observe_auv(x, y, psi, u, v, r, heading_target, perr_x, perr_y, herr, obs);
+        observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, perr_x, perr_y, herr, obs);
     }
+    a.target[i] = heading_target;
+    if (P.cyl) a.iwp[i] = iwp;
     a.state[i] = x; a.state[ld + i] = y; a.state[2 * ld + i] = psi;
     a.state[3 * ld + i] = u; a.state[4 * ld + i] = v; a.state[5 * ld + i] = r;
     a.err_o[i] = perr_x; a.err_o[ld + i] = perr_y; a.err_o[2 * ld + i] = herr;
@@ -296,6 +318,7 @@ template <typename T> struct AuvResetArgs {
     AuvDev<T> P;
     long n, ld;
     T* state; T* obs; int32_t* istep; T* mults; T* target; T* err_o; T* recent; T* ep_return;
+    const int32_t* iwp;
     const uint32_t* episode; const uint8_t* mask;
     const T* init;  // nullable [4][ld]: x, y, heading, headingTarget (fixedInitialValues)
     unsigned long long seed, env_id0;
@@ -313,6 +336,8 @@ auv_reset_kernel(const __grid_constant__ AuvResetArgs<T> a) {
     T mm[11], x, y, psi, target, offset;
     draw_reset_auv(a.P, a.seed, a.env_id0 + (unsigned long long)i, a.episode ? a.episode[i] : 0u, a.apply_noise != 0, mm, &x, &y, &psi, &target, &offset);
     if (a.init != nullptr) { x = a.init[i]; y = a.init[ld + i]; psi = a.init[2 * ld + i]; target = a.init[3 * ld + i]; }
+    T tx = T(0), ty = T(0);
+    if (a.P.cyl) { const int w = a.iwp[i]; tx = a.P.wp[w][0]; ty = a.P.wp[w][1]; target = a.P.wp[w][2]; }
 #pragma unroll
     for (int k = 0; k < 11; ++k) a.mults[k * ld + i] = mm[k];
     a.state[i] = x; a.state[ld + i] = y; a.state[2 * ld + i] = psi;
@@ -323,9 +348,9 @@ auv_reset_kernel(const __grid_constant__ AuvResetArgs<T> a) {
 #pragma unroll
     for (int k = 0; k < 30; ++k) a.recent[k * ld + i] = T(0);
     const T herr = angle_error(target, psi);
-    a.err_o[i] = -x; a.err_o[ld + i] = -y; a.err_o[2 * ld + i] = herr;
+    a.err_o[i] = tx - x; a.err_o[ld + i] = ty - y; a.err_o[2 * ld + i] = herr;
     T obs[11];
-    observe_auv(x, y, psi, T(0), T(0), T(0), target, -x, -y, herr, obs);
+    observe_auv(a.P.cyl != 0, tx, ty, x, y, psi, T(0), T(0), T(0), target, tx - x, ty - y, herr, obs);
 #pragma unroll
     for (int k = 0; k < 11; ++k) a.obs[k * ld + i] = obs[k];
 }

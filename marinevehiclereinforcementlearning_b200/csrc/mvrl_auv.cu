@@ -27,6 +27,8 @@ extern "C" MVRL_API int mvrl_auv_default_params(MvrlAuvParams* p) {
     p->maxForce = 150.; p->maxMoment = 20.;
     p->xMin = -1.; p->xMax = 1.; p->yMin = -1.; p->yMax = 1.;
     p->noiseMagCoeffs = 0.; p->noiseMagActuation = 0.;
+    p->variant = MVRL_AUV_PLAIN; p->n_waypoints = 0; p->wp_threshold = 0.;
+    memset(p->waypoints, 0, sizeof(p->waypoints));
     return MVRL_OK;
 }
 
@@ -34,6 +36,9 @@ extern "C" MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* para
     if (!out || !params || !cfg) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_create: null argument");
     if (cfg->dtype != MVRL_F32 && cfg->dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "dtype must be MVRL_F32 or MVRL_F64");
     if (!(cfg->dt > 0)) return mvrl_fail(MVRL_EINVAL, "dt must be > 0");
+    if (params->variant == MVRL_AUV_CYL && (params->n_waypoints < 1 || params->n_waypoints > 32))
+        return mvrl_fail(MVRL_EINVAL, "AuvEnvCyl needs 1..32 way-points");
+    if (params->variant != MVRL_AUV_CYL && params->variant != MVRL_AUV_PLAIN) return mvrl_fail(MVRL_EINVAL, "bad variant");
     { const int rc = mvrl_require_device(cfg->device); if (rc != MVRL_OK) return rc; }
     MvrlAuv* h = new (std::nothrow) MvrlAuv();
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
@@ -67,6 +72,8 @@ template <typename T> static AuvDev<T> auv_dev(const MvrlAuv* h) {
     d.xmin = T(p.xMin); d.xmax = T(p.xMax); d.ymin = T(p.yMin); d.ymax = T(p.yMax);
     d.noise_coeffs = T(p.noiseMagCoeffs); d.noise_act = T(p.noiseMagActuation);
     d.t_quarter = T((double)(h->nt / 4) * h->dtf);  // flow.time[nt // 4], verySimpleAuv.py:245
+    d.cyl = p.variant == MVRL_AUV_CYL ? 1 : 0; d.n_wp = p.n_waypoints; d.wp_thr = T(p.wp_threshold);
+    for (int k = 0; k < 32; ++k) for (int j = 0; j < 3; ++j) d.wp[k][j] = T(k < p.n_waypoints ? p.waypoints[k * 3 + j] : 0.);
     return d;
 }
 
@@ -77,6 +84,7 @@ template <typename T> static int auv_step_impl(const MvrlAuv* h, int64_t n, int6
     a.n = n; a.ld = ld;
     a.state = (T*)b->state; a.action = (const T*)b->action; a.obs = (T*)b->obs; a.reward = (T*)b->reward; a.done = b->done; a.istep = b->istep;
     a.mults = (T*)b->mults; a.target = (T*)b->target; a.err_o = (T*)b->err_o; a.recent = (T*)b->recent; a.ep_return = (T*)b->ep_return;
+    a.iwp = b->iwp;
     a.episode = b->episode; a.term_obs = (T*)b->terminal_obs; a.aux = (T*)b->aux; a.stats = b->ep_stats;
     a.dt = T(h->c.dt); a.max_steps = h->c.max_steps; a.seed = h->c.seed; a.env_id0 = h->c.env_id0;
     a.auto_reset = h->c.auto_reset; a.stop_on_bounds = h->c.stop_on_bounds; a.apply_noise = h->c.apply_noise;
@@ -98,6 +106,7 @@ extern "C" MVRL_API int mvrl_auv_step(MvrlAuv* h, int64_t n, int64_t ld, const M
     if (!b->state || !b->action || !b->obs || !b->reward || !b->done || !b->istep || !b->mults || !b->target || !b->err_o || !b->recent || !b->ep_return)
         return mvrl_fail(MVRL_EINVAL, "mvrl_auv_step: missing required buffer");
     if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_step: episode is required with auto_reset");
+    if (h->p.variant == MVRL_AUV_CYL && !b->iwp) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_step: iwp is required for the AuvEnvCyl variant");
     if (n == 0) return MVRL_OK;
     MVRL_CUDA(cudaSetDevice(h->c.device));
     if (h->c.dtype == MVRL_F64) return auv_step_impl<double>(h, n, ld, b, (cudaStream_t)stream);
@@ -109,7 +118,7 @@ template <typename T> static int auv_reset_impl(const MvrlAuv* h, int64_t n, int
     a.P = auv_dev<T>(h);
     a.n = n; a.ld = ld;
     a.state = (T*)b->state; a.obs = (T*)b->obs; a.istep = b->istep; a.mults = (T*)b->mults; a.target = (T*)b->target; a.err_o = (T*)b->err_o;
-    a.recent = (T*)b->recent; a.ep_return = (T*)b->ep_return; a.episode = b->episode; a.mask = mask; a.init = (const T*)init;
+    a.recent = (T*)b->recent; a.ep_return = (T*)b->ep_return; a.iwp = b->iwp; a.episode = b->episode; a.mask = mask; a.init = (const T*)init;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0; a.apply_noise = h->c.apply_noise;
     auv_reset_kernel<T><<<mvrl_grid_for(n, 128), 128, 0, s>>>(a);
     return mvrl_check_launch("auv_reset");
@@ -121,6 +130,7 @@ extern "C" MVRL_API int mvrl_auv_reset(MvrlAuv* h, int64_t n, int64_t ld, const 
     if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_reset: need 0 <= n <= ld");
     if (!b->state || !b->obs || !b->istep || !b->mults || !b->target || !b->err_o || !b->recent || !b->ep_return)
         return mvrl_fail(MVRL_EINVAL, "mvrl_auv_reset: missing required buffer");
+    if (h->p.variant == MVRL_AUV_CYL && !b->iwp) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_reset: iwp is required for the AuvEnvCyl variant");
     if (n == 0) return MVRL_OK;
     MVRL_CUDA(cudaSetDevice(h->c.device));
     if (h->c.dtype == MVRL_F64) return auv_reset_impl<double>(h, n, ld, b, mask, init, (cudaStream_t)stream);

@@ -92,9 +92,11 @@ class AuvEnv(Env):
     _COEFFS = ("m", "Izz", "Xuu", "Yvv", "Nrr", "Xu", "Yv", "Nr", "maxForce", "maxMoment", "noiseMagCoeffs", "noiseMagActuation",
                "stopOnBoundsExceeded", "_max_episode_steps", "dt")
 
+    _VEC = AuvVecEnv
+
     def _engine(self):
         if self._vec is None:
-            self._vec = AuvVecEnv(1, self.flow, seed=0 if self.seed is None else int(self.seed), dt=self.dt, dtype=self.flow.dtype,
+            self._vec = self._VEC(1, self.flow, seed=0 if self.seed is None else int(self.seed), dt=self.dt, dtype=self.flow.dtype,
                                   auto_reset=False, record_aux=True, record_terminal_obs=False)
         v = self._vec
         for name in self._COEFFS:  # attributes edited on the env (as reference users do) reach the kernel
@@ -125,9 +127,9 @@ class AuvEnv(Env):
         m = v._mults[:, 0].cpu().numpy()
         (self.mMult, self.IMult, self.XuuMult, self.YvvMult, self.NrrMult, self.XuMult, self.YvMult, self.NrMult,
          self.XactMult, self.YactMult, self.NactMult) = (float(x) for x in m)
+        self.positionTarget = np.zeros(2)
         self.headingTarget = float(v.headingTarget[0])
         self.flowDataTimeOffset = float(v.flowDataTimeOffset[0])
-        self.positionTarget = np.zeros(2)
         self.time = 0
         self.iStep = 0
         self.steps_beyond_done = 0

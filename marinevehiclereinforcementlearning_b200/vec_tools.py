@@ -67,7 +67,7 @@ class TrajectoryRecorder:
         if self.kind in ("rov6", "rov3"):
             return torch.cat([t, e._state[:, :k], e._aux[:, :k], e._setpoint[:, :k]])
         s, aux = e._state[:, :k], e._aux[:, :k]
-        zeros = torch.zeros((2, k), dtype=e.dtype, device=e.device)
+        zeros = e.positionTarget[:k].T if hasattr(e, "positionTarget") else torch.zeros((2, k), dtype=e.dtype, device=e.device)
         act = self._last_actions if self._last_actions is not None else torch.zeros((3, k), dtype=e.dtype, device=e.device)
         return torch.cat([e._istep[:k].to(e.dtype).unsqueeze(0), t, e._reward[:k].unsqueeze(0), s[0:3], zeros, e._target[0:1, :k],
                           aux[0:6], s[3:6], aux[6:9], aux[9:14], act, e._obs[:, :k]])

@@ -895,6 +895,10 @@ class AuvEnvOracle:
                          c(self.velocities[:, 0]), c(self.velocities[:, 1]), c(self.velocities[:, 2]),
                          np.zeros(self.n), np.zeros(self.n)], axis=1)
 
+    def _errors(self, position, heading):
+        """perr, herr of legacy/verySimpleAuv.py:344-346 (positionTarget = 0)."""
+        return -position, angle_error(self.heading_target, heading)
+
     def step(self, action):
         """legacy/verySimpleAuv.py:264-410."""
         action = np.atleast_2d(np.asarray(action, dtype=float))
@@ -930,8 +934,7 @@ class AuvEnvOracle:
         bonus += -100. * out_x + -100. * out_y
         if self.stop_on_bounds:
             done = done | out_x | out_y
-        perr = -position
-        herr = angle_error(self.heading_target, heading)
+        perr, herr = self._errors(position, heading)
         self.herr_o, self.perr_o = herr, perr
         # population std of the <= 10 most recent actions, mean over the 3 components (:353-355)
         cnt = self.n_recent[:, None, None]
@@ -996,3 +999,60 @@ def los_navigation_predict(obs, rnav=0.5):
     obs = np.atleast_2d(np.asarray(obs, dtype=float))
     tp = line_of_sight(obs[:, 0:2], obs[:, 2:4], rnav)
     return np.concatenate([tp, obs[:, 4:5]], axis=1)
+
+
+# ==========================================================================
+# legacy: AuvEnvCyl (legacy/verySimpleAuv_cyl.py:22-345) - way-point following around a cylinder
+# ==========================================================================
+def cyl_waypoints(Rcyl=1.33, xCyl=(2.5, 0.)):
+    """legacy/verySimpleAuv_cyl.py:29-41 -> ([21, 3] way-points x, y, target heading; switch threshold)."""
+    Rwp = Rcyl * 1.3
+    t = np.linspace(-30, 30, 21) * np.pi / 180.
+    return np.vstack([-Rwp * np.cos(t) + xCyl[0], Rwp * np.sin(t) + xCyl[1], -t]).T, Rcyl * 0.05
+
+
+class AuvCylEnvOracle(AuvEnvOracle):
+    """Differences to AuvEnv: position / heading targets follow a way-point list (the index ``iWp`` advances when
+    the vehicle is within ``wpThreshold`` and is NOT reset between episodes - it lives in ``__init__`` only,
+    :41), V0 observation scaling (:99-112), bounds +-2 (:69-70), 1200-step episodes (:44), and reset draws no
+    heading target (:155-160), i.e. 15 uniforms instead of 16."""
+
+    def __init__(self, n, flow, max_steps=1200, **kw):
+        super().__init__(n, flow, max_steps=max_steps, **kw)
+        self.xMinMax, self.yMinMax = [-2, 2], [-2, 2]
+        self.waypoints, self.wp_threshold = cyl_waypoints()
+        self.i_wp = np.zeros(n, dtype=np.int64)
+
+    def _draw(self, idx, apply_noise=True):
+        u = philox_uniform(self.seed, self.env_ids[idx], self.episode[idx], 15)
+        mults = np.ones((len(idx), 11))
+        if apply_noise:
+            mults[:, :8] = 1. + self.noiseMagCoeffs / 2. - u[:, :8] * self.noiseMagCoeffs
+            mults[:, 8:] = 1. + self.noiseMagActuation / 2. - u[:, 8:11] * self.noiseMagActuation
+        pos = (u[:, 11:13] - 0.5) * 0.5 * np.array([self.xMinMax[1] - self.xMinMax[0], self.yMinMax[1] - self.yMinMax[0]])
+        heading = u[:, 13] * TWO_PI
+        offset = u[:, 14] * self.flow.time[self.flow.time.shape[0] // 4]
+        return mults, pos, heading, self.waypoints[self.i_wp[idx], 2], offset
+
+    def _install(self, idx, mults, pos, heading, target, offset):
+        super()._install(idx, mults, pos, heading, self.waypoints[self.i_wp[idx], 2], offset)
+        self.perr_o[idx] = self.waypoints[self.i_wp[idx], :2] - self.position[idx]
+
+    def observe(self):
+        """legacy/verySimpleAuv_cyl.py:84-115 (V0 scaling)."""
+        perr = self.waypoints[self.i_wp, :2] - self.position
+        herr = angle_error(self.heading_target, self.heading)
+        c = lambda x: np.minimum(1., np.maximum(-1., x))
+        return np.stack([c(perr[:, 0] / 0.2), c(perr[:, 1] / 0.2), c(herr / (45. / 180. * np.pi)),
+                         c((herr - self.herr_o) / (2. / 180 * np.pi)), c((perr[:, 0] - self.perr_o[:, 0]) / 0.025),
+                         c((perr[:, 1] - self.perr_o[:, 1]) / 0.025), c(self.velocities[:, 0] / 0.2), c(self.velocities[:, 1] / 0.2),
+                         c(self.velocities[:, 2] / (30. / 180. * np.pi)), np.zeros(self.n), np.zeros(self.n)], axis=1)
+
+    def _errors(self, position, heading):
+        """perr / herr against the CURRENT way-point, then the way-point switch (:243-254)."""
+        perr = self.waypoints[self.i_wp, :2] - position
+        herr = angle_error(self.heading_target, heading)
+        reached = np.sqrt(perr[:, 0] ** 2 + perr[:, 1] ** 2) < self.wp_threshold
+        self.i_wp = np.where(reached, np.minimum(self.waypoints.shape[0] - 1, self.i_wp + 1), self.i_wp)
+        self.heading_target = self.waypoints[self.i_wp, 2].copy()
+        return perr, herr

@@ -202,3 +202,80 @@ def test_non_finite_positions_do_not_fault():
         out = flow.interp(t, xy)
         torch.cuda.synchronize()
         assert out.shape == (3, 3)
+
+
+# ---------------------------------------------------------------- AuvEnvCyl ----
+def cyl_flows(dtype=torch.float64):
+    g = load_golden("legacy")
+    return make_flows(g, dtype, smooth=True)      # the long-wave field gen_golden_legacy_cyl.py used
+
+
+def test_cyl_episodes_fp64_vs_reference_golden():
+    """AuvEnvCyl (verySimpleAuv_cyl.py) through the kernels: way-point switch, way-point index carried across
+    episodes, V0 observation scaling, bounds +-2 - against episodes of the unmodified reference."""
+    from marinevehiclereinforcementlearning_b200 import AuvCylVecEnv
+    g = load_golden("legacy_cyl")
+    flow, _ = cyl_flows()
+    assert abs(flow.dt - float(g["flow_dt"])) < 1e-18
+    env = AuvCylVecEnv(1, flow, dtype=torch.float64, noiseMagCoeffs=0.1, noiseMagActuation=0.1, auto_reset=False, record_aux=True)
+    assert np.abs(env.waypoints - g["waypoints"]).max() < 1e-15 and env.wpThreshold == float(g["wp_threshold"])
+    for e in range(g["ep_actions"].shape[0]):
+        assert int(env.iWp[0]) == int(g["ep_iwp0"][e])
+        env.reset(applyNoise=False, fixedInitialValues=[g["ep_pos0"][e], float(g["ep_heading0"][e])])
+        env._mults[:, 0] = torch.as_tensor(g["ep_mults"][e], device=DEV)
+        env._target[1, 0] = float(g["ep_t_offset"][e])
+        assert np.abs(env.state.cpu().numpy()[0] - g["ep_obs0"][e]).max() < 1e-13
+        for k in range(g["ep_actions"].shape[1]):
+            ob, r, d, _ = env.step(torch.as_tensor(g["ep_actions"][e, k:k + 1], device=DEV))
+            assert np.abs(ob.cpu().numpy()[0] - g["ep_obs"][e, k]).max() < 1e-8, (e, k)
+            assert abs(float(r[0]) - g["ep_reward"][e, k]) < 1e-8, (e, k)
+            assert bool(d[0]) == bool(g["ep_done"][e, k]) and int(env.iWp[0]) == int(g["ep_iwp"][e, k]), (e, k)
+            h = g["ep_history"][e, k]
+            assert np.abs(env.positionTarget.cpu().numpy()[0] - h[6:8]).max() < 1e-14 and abs(float(env.headingTarget[0]) - h[8]) < 1e-14
+            if d[0]:
+                break
+
+
+def test_cyl_single_env_dropin_and_batched_vs_oracle():
+    from marinevehiclereinforcementlearning_b200 import AuvCylVecEnv
+    from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence import verySimpleAuv_cyl
+    g = load_golden("legacy_cyl")
+    flow, rflow = cyl_flows()
+    # reference-shaped class: episode 1 of the golden file starts from fixed values (only the time offset was random)
+    single_flow = flowGenerator.ReconstructedFlow.from_base_field(smooth_base_field(load_golden("legacy")), dtype=torch.float64, device=DEV)
+    env = verySimpleAuv_cyl.AuvEnvCyl(noiseMagCoeffs=0.1, noiseMagActuation=0.1, flow=single_flow)
+    assert env._max_episode_steps == 1200 and env.xMinMax == [-2, 2] and env.waypoints.shape == (21, 3)
+    e = 3   # applyNoise=False, fixed start next to the boundary -> bounds termination; way-point index 1 at that time
+    env.reset(applyNoise=False, fixedInitialValues=[np.array([1.97, -1.9]), 2.0, None])
+    env._vec._iwp[0] = int(g["ep_iwp0"][e])
+    ob0 = env.reset(applyNoise=False, fixedInitialValues=[np.array([1.97, -1.9]), 2.0, None])
+    env._vec._target[1, 0] = float(g["ep_t_offset"][e])
+    assert np.abs(ob0 - g["ep_obs0"][e]).max() < 1e-13 and env.iWp == 1
+    for k in range(g["ep_actions"].shape[1]):
+        ob, r, d, info = env.step(g["ep_actions"][e, k])
+        assert np.abs(ob - g["ep_obs"][e, k]).max() < 1e-8 and abs(r - g["ep_reward"][e, k]) < 1e-8
+        if d:
+            break
+    assert d and k == 3
+    hist = env.timeHistory.values
+    assert hist.shape == (4, 40) and rel_err(hist, g["ep_history"][e, :4]) < 1e-8
+    # batched, auto-reset, two shards, vs the oracle
+    n, steps = 256, 60
+    rng = np.random.default_rng(61)
+    acts = rng.uniform(-1, 1, (steps, n, 3)) * 0.5
+    kw = dict(noiseMagCoeffs=0.1, noiseMagActuation=0.1, maxSteps=25, auto_reset=True, seed=4)
+    full = AuvCylVecEnv(n, flow, dtype=torch.float64, **kw)
+    a = AuvCylVecEnv(n // 2, flow, dtype=torch.float64, env_id0=0, **kw)
+    b = AuvCylVecEnv(n // 2, flow, dtype=torch.float64, env_id0=n // 2, **kw)
+    ref = o.AuvCylEnvOracle(n, rflow, noiseMagCoeffs=0.1, noiseMagActuation=0.1, max_steps=25, auto_reset=True, seed=4)
+    assert np.abs(full.reset().cpu().numpy() - ref.reset()).max() < 1e-12
+    a.reset(); b.reset()
+    for k in range(steps):
+        act = torch.as_tensor(acts[k], device=DEV)
+        obs, rew, done, info = full.step(act)
+        oa, ra, da, _ = a.step(act[: n // 2]); ob, rb, db, _ = b.step(act[n // 2:])
+        assert torch.equal(obs, torch.cat([oa, ob])) and torch.equal(rew, torch.cat([ra, rb])) and torch.equal(done, torch.cat([da, db]))
+        ro, rr, rd, _ = ref.step(acts[k])
+        assert np.array_equal(done.cpu().numpy(), rd), k
+        assert np.abs(obs.cpu().numpy() - ro).max() < 1e-9 and np.abs(rew.cpu().numpy() - rr).max() < 1e-8, k
+        assert np.array_equal(full.iWp.cpu().numpy(), ref.i_wp)

@@ -44,7 +44,8 @@ def test_auv_native_constants_and_layout(lib):
     assert (p.m, p.Izz, p.maxForce, p.maxMoment) == (11.4, 0.16, 150., 20.)
     assert p.Xuu == -18.18 * 2.21 and p.Yvv == -21.66 * 4.87 and p.Xu == -4.03 * 2.21 and p.Yv == -6.22 * 4.87
     assert (p.xMin, p.xMax, p.yMin, p.yMax) == (-1., 1., -1., 1.)
-    assert C.sizeof(_lib.MvrlAuvParams) == 16 * 8 and C.sizeof(_lib.MvrlAuvBuffers) == 15 * 8
+    assert C.sizeof(_lib.MvrlAuvParams) == (17 + 96) * 8 + 8 and C.sizeof(_lib.MvrlAuvBuffers) == 16 * 8
+    assert p.variant == 0 and p.n_waypoints == 0
     assert C.sizeof(_lib.MvrlAuvConfig) == 4 + 4 + 8 + 8 + 8 + 4 * 4
 
 

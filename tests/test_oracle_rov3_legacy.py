@@ -135,3 +135,41 @@ def test_los_navigation_oracle_vs_reference_golden():
     t = o.line_of_sight(g["los_p0"], g["los_p1"], g["los_rnav"])
     assert np.abs(t - g["los_target"]).max() < 1e-14 and not np.isnan(t).any()
     assert np.abs(o.los_navigation_predict(g["nav_obs"]) - g["nav_action"]).max() < 1e-14
+
+
+def make_modes_flow(nt=48):
+    g = load_golden("legacy")
+    rng = np.random.default_rng(3)
+    ny, nx, _ = g["ltm"].shape
+    t, y, x = np.meshgrid(np.arange(nt), np.arange(ny), np.arange(nx), indexing="ij")
+    f = np.repeat(g["ltm"][None], nt, axis=0).copy()
+    for c in range(3):
+        for _ in range(4):
+            kt, ky, kx = rng.uniform(0.05, 0.3), rng.uniform(0.02, 0.12), rng.uniform(0.02, 0.12)
+            f[..., c] += 0.02 * np.sin(kt * t + ky * y + kx * x + rng.uniform(0, 2 * np.pi))
+    flow = o.FlowOracle(f, float(g["base_dx"]), float(g["base_dy"]), float(g["base_dt"]))
+    flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    return flow
+
+
+def test_auv_cyl_episodes_vs_reference_golden():
+    """AuvEnvCyl (legacy/verySimpleAuv_cyl.py): way-point switch, iWp carried across episodes, V0 observation scaling."""
+    g = load_golden("legacy_cyl")
+    flow = make_modes_flow()
+    assert abs(flow.dt - float(g["flow_dt"])) < 1e-18
+    wps, thr = o.cyl_waypoints()
+    assert np.abs(wps - g["waypoints"]).max() < 1e-15 and thr == float(g["wp_threshold"])
+    env = o.AuvCylEnvOracle(1, flow, noiseMagCoeffs=0.1, noiseMagActuation=0.1)
+    env.reset()
+    for e in range(g["ep_actions"].shape[0]):
+        assert env.i_wp[0] == g["ep_iwp0"][e]          # never reset between episodes, as upstream
+        ob0 = env.set_initial(g["ep_mults"][e:e + 1], g["ep_pos0"][e:e + 1], g["ep_heading0"][e:e + 1], None, g["ep_t_offset"][e:e + 1])
+        assert np.abs(ob0[0] - g["ep_obs0"][e]).max() < 1e-13
+        for k in range(g["ep_actions"].shape[1]):
+            ob, r, d, _ = env.step(g["ep_actions"][e, k:k + 1])
+            assert np.abs(ob[0] - g["ep_obs"][e, k]).max() < 1e-9, (e, k)
+            assert abs(r[0] - g["ep_reward"][e, k]) < 1e-9, (e, k)
+            assert bool(d[0]) == bool(g["ep_done"][e, k]) and env.i_wp[0] == g["ep_iwp"][e, k]
+            if d[0]:
+                break
+    assert g["ep_iwp"].max() >= 1   # the golden episodes do contain a way-point switch
