@@ -427,6 +427,43 @@ def run_auv(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_rov3(args, rank, local_rank, world):
+    """Config 1's model at scale: BlueROV2 Heavy 3DoF env, fp32, 1 Mi envs per GPU, dt = 0.2 as nSub RK4 sub-steps,
+    auto-reset; --action-mode setpoint = the reference's Gym semantics (built-in PID), rpm = 4 thruster rpm."""
+    import torch
+    import torch.distributed as dist
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy3DoFVecEnv
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, mode = args.envs, ("rpm" if args.action_mode == "rpm" else "setpoint")
+    na, scale = (4, 3500.0) if mode == "rpm" else (3, 1.0)
+    env = BlueROV2Heavy3DoFVecEnv(n, action_mode=mode, dtype=torch.float32, device=dev, dt=DT, maxSteps=MAX_STEPS, n_sub=args.n_sub,
+                                  seed=1234, env_id0=rank * n, auto_reset=True, record_terminal_obs=False)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = [(torch.rand((na, env.ld), generator=gen, device=dev) * 2 - 1) * scale for _ in range(8)]
+    env._istep.copy_((torch.arange(env.ld, device=dev) % MAX_STEPS).to(torch.int32))
+
+    def one_step(k):
+        env._bufs.action = acts[k % 8].data_ptr()
+        env.step_async()
+    ms, clocks = _timed(dev, world, one_step, args.steps, args.warmup)
+    stats = env.episode_stats()
+    if rank == 0:
+        rate = n / (ms / args.steps * 1e-3)
+        line = {"metric": "BlueROV2 3DoF env-steps/sec", "value": world * rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "rov3_step fp32: BlueROV2 Heavy 3DoF, %d envs/GPU, %s actions, dt=%.1f as nSub=%d RK4, maxSteps=%d auto-reset"
+                                       % (n, mode, DT, args.n_sub, MAX_STEPS)},
+                "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_rollout(args, rank, local_rank, world):
     """Config 5: rollout collection over the 6DoF env in the reference's Gym semantics (PID set-point actions):
     131 072 envs per GPU, policy MLP 9-128-128-128-6 (GELU, arch of legacy/main_00_sbl.py:100-105) + Gaussian head in
@@ -528,8 +565,8 @@ def main():
     ap.add_argument("--action-mode", default="rpm", choices=["rpm", "force", "setpoint"], help="default rpm = BASELINE config 3")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--n-sub", type=int, default=N_SUB)
-    ap.add_argument("--workload", default="rov6", choices=["rov6", "auv", "rollout"],
-                    help="rov6 = BASELINE config 3 (the metric); auv = config 4; rollout = config 5")
+    ap.add_argument("--workload", default="rov6", choices=["rov6", "rov3", "auv", "rollout"],
+                    help="rov6 = BASELINE config 3 (the metric); rov3 = the 3DoF env at scale; auv = config 4; rollout = config 5")
     ap.add_argument("--field", default="modes", choices=["modes", "noise"], help="auv: synthetic turbulence stand-in")
     ap.add_argument("--rollout-len", type=int, default=128)
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
@@ -543,6 +580,8 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "rov3":
+        run_rov3(args, rank, local_rank, world)
     elif args.workload == "auv":
         run_auv(args, rank, local_rank, world)
     elif args.workload == "rollout":

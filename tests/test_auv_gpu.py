@@ -279,3 +279,39 @@ def test_cyl_single_env_dropin_and_batched_vs_oracle():
         assert np.array_equal(done.cpu().numpy(), rd), k
         assert np.abs(obs.cpu().numpy() - ro).max() < 1e-9 and np.abs(rew.cpu().numpy() - rr).max() < 1e-8, k
         assert np.array_equal(full.iWp.cpu().numpy(), ref.i_wp)
+
+
+def test_spod_reconstruction_constructor(tmp_path):
+    """ReconstructedFlow(dataDir) (flowGenerator.py:13-51): the blobs are absent upstream, so the loader is
+    exercised with small synthetic files of the same layout; the reconstruction (one device GEMM) must equal the
+    reference's per-time-level expression  real(modes @ coeffs[:, t]) + mean."""
+    import yaml
+    rng = np.random.default_rng(5)
+    ny, nx, nf, nm, nt = 7, 9, 3, 6, 11
+    modes = rng.standard_normal((ny, nx, nf, nm)) + 1j * rng.standard_normal((ny, nx, nf, nm))
+    coeffs = rng.standard_normal((nm, nt)) + 1j * rng.standard_normal((nm, nt))
+    ltm = rng.standard_normal((ny, nx, nf))
+    xs, ys = np.arange(nx) * 0.005, np.arange(ny) * 0.005
+    coords = np.stack(np.meshgrid(xs, ys), axis=2)
+    d = str(tmp_path)
+    np.save(d + "/modes_r.npy", modes); np.save(d + "/coeffs.npy", coeffs); np.save(d + "/ltm.npy", ltm)
+    np.save(d + "/turbulence_coords.npy", coords)
+    with open(d + "/params_coeffs.yaml", "w") as fh:
+        yaml.safe_dump({"time_step": 0.002, "n_modes_save": nm}, fh)
+    flow = flowGenerator.ReconstructedFlow(d, dtype=torch.float64, device=DEV)
+    want = np.stack([np.real(np.matmul(modes, coeffs[:, t])) + ltm for t in range(nt)])   # flowGenerator.py:20-23
+    assert flow.shape == (nt, ny, nx, nf) and np.abs(flow.baseFlowData.cpu().numpy() - want).max() < 1e-12
+    assert flow.baseDt == 0.002 and abs(flow.baseDx - 0.005) < 1e-15 and abs(flow.baseDy - 0.005) < 1e-15
+    ref = o.FlowOracle(want, 0.005, 0.005, 0.002)
+    flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1)); ref.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+    t = rng.uniform(0, ref.time[-1], 50); xy = rng.uniform(0, 0.3, (50, 2))
+    assert rel_err(flow.interp(torch.as_tensor(t, device=DEV), torch.as_tensor(xy, device=DEV)).cpu().numpy(), ref.interp(t, xy)) < 1e-11
+    uP = np.sqrt(np.sum((want[..., 0] - 1.) ** 2., axis=0) / nt)                              # flowGenerator.py:47-51
+    assert np.abs(flow.uPrime - uP).max() < 1e-12 and flow.TI.shape == (ny, nx)
+    coords_bad = coords.copy(); coords_bad[0, 3, 0] += 1e-3
+    np.save(d + "/turbulence_coords.npy", coords_bad)
+    with pytest.raises(ValueError):
+        flowGenerator.ReconstructedFlow(d, dtype=torch.float64, device=DEV)
+    os_missing = str(tmp_path / "nothing_here")
+    with pytest.raises(FileNotFoundError):
+        flowGenerator.ReconstructedFlow(os_missing)
