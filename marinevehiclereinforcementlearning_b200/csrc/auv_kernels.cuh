@@ -67,7 +67,6 @@ __device__ __forceinline__ void flow_interp(const FlowDev<T>& f, T time, T x, T 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // issue: 8 x 8-byte copies (2 time levels x 2 rows x 2 x-neighbours) into slot[8] of this thread
 __device__ __forceinline__ void flow_stage_issue(const FlowDev<float>& f, const FlowCell<float>& c, float2 (*slot)[MVRL_AUV_BLOCK]) {

@@ -142,6 +142,8 @@ template <typename T> __device__ __forceinline__ void rk4_pose_update(T& y, T& c
     y = s;
 }
 
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- Philox4x32-10 ---------------------------------------------------------
 struct Philox {
     static __device__ __forceinline__ uint4 run(uint4 c, uint2 k) {

@@ -204,6 +204,13 @@ template <typename V, typename S> __device__ __forceinline__ V load_v(const S* p
     if constexpr (VT<V>::L == 1) { (void)pair; return p[i0]; }
     else { if (pair) return f2_from(*reinterpret_cast<const float2*>(p + i0)); return F2(p[i0], 0.0f); }
 }
+// asynchronous global -> shared copy of one thread's element(s) of a row (4 / 8 bytes)
+template <typename V, typename S> __device__ __forceinline__ void cp_async_v(V* smem, const S* gmem, bool pair) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    if (sizeof(V) == 8 && (VT<V>::L == 1 || pair)) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem));
+}
+
 template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, long i0, bool pair, V x) {
     if constexpr (VT<V>::L == 1) { (void)pair; p[i0] = x; }
     else { if (pair) *reinterpret_cast<float2*>(p + i0) = x.v; else p[i0] = x.v.x; }
@@ -229,10 +236,12 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     V act[NA];
 #pragma unroll
     for (int k = 0; k < NA; ++k) act[k] = load_v<V>(a.action + k * ld, i0, pair);
-    // needed by the epilogue only, but issued here so that their DRAM latency hides behind the RK4 loop
-    V path_v[6];
+    // Needed by the epilogue only: the way-points are copied global -> shared with cp.async (LDGSTS) now, so their
+    // DRAM latency hides behind the RK4 loop without holding 6 (12) registers across it - as registers they were
+    // spilled (r1i profile: STL in the prologue and LDL / long-scoreboard stalls in the epilogue).
+    __shared__ V s_path[6][StepLaunch<V>::BLOCK];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) path_v[k] = load_v<V>(a.path + k * ld, i0, pair);
+    for (int k = 0; k < 6; ++k) cp_async_v<V>(&s_path[k][threadIdx.x], a.path + k * ld + i0, pair);
     int istep_in[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) istep_in[l] = (l == 0 || pair) ? a.istep[i0 + l] : 0;
@@ -355,6 +364,10 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     // ---- epilogue: wrap, observe, done, stats - straight-line for every environment of the thread; the
     // auto-reset of a terminated environment is an out-of-line fix-up AFTER the regular stores (it overwrites
     // that environment's rows; same thread, so program order makes the later stores win) ----
+    cp_async_wait_all();     // each thread reads back only its own slots: no barrier needed
+    V path_v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) path_v[k] = s_path[k][threadIdx.x];
     V nonfinite = V(T(0));   // sum of 0 * y_k: 0 when every state is finite, NaN otherwise
 #pragma unroll
     for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
