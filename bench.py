@@ -288,7 +288,8 @@ def run_ours(args, rank, local_rank, world):
     h2d = n * na * w
     d2h = n * (9 * w + w + 1)
     # launches inside the device-timed region: one fused step kernel per bench step
-    e2e_launches_per_step = 3 * args.e2e_chunks
+    e2e_pieces = _lib.load().mvrl_host_chunk_count(n, args.e2e_chunks)
+    e2e_launches_per_step = 3 * e2e_pieces
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -324,9 +325,9 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "inputs larger than L2: ~125 MB touched per step + 4 rotating 32 MiB action batches"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "chunks": args.e2e_chunks, "gpu_launches_per_step": e2e_launches_per_step,
+                        "chunks": e2e_pieces, "gpu_launches_per_step": e2e_launches_per_step,
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
-                                "chunked H2D / transpose / fused step / transpose / D2H pipeline"},
+                                "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, reward + done stored into the pinned host arrays by the transpose kernel)"},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
         print(json.dumps(line))
     if world > 1:
@@ -561,7 +562,7 @@ def main():
     ap.add_argument("--fast-math", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=100)
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="pieces of the host-buffer pipeline; 0 = the library's default")
     ap.add_argument("--action-mode", default="rpm", choices=["rpm", "force", "setpoint"], help="default rpm = BASELINE config 3")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--n-sub", type=int, default=N_SUB)

@@ -164,14 +164,21 @@ MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t
 /* One env step with HOST buffers - the call a host-side VecEnv user makes (BlueROV2Heavy6DoFEnv.step for n
  * vehicles, 6DoF.py:531-594): actions_host T [n][A] (row = environment) in; obs_host T [n][9], reward_host
  * T [n] (nullable), done_host [n] (nullable) out.  Pinned host memory is needed for the copies to overlap.
- * The batch is cut into `chunks` pieces (0: default 4); upload, transpose to SoA, fused step, transpose
- * back and download of different pieces overlap on streams owned by the handle (PCIe is full duplex).
+ * The batch is cut into `chunks` equal pieces (0: the default, 8); upload, transpose to SoA, fused step, transpose
+ * back and download of different pieces overlap on streams owned by the handle (PCIe is full duplex).  The
+ * observations travel by copy engine; reward and done flags (5 B per environment) are stored straight into
+ * reward_host / done_host by the transpose kernel when those arrays are pinned, so that the download engine has
+ * one copy per piece to do (pageable arrays: copied like the observations).
  * The whole pipeline is captured into a CUDA graph once per distinct set of pointers (4 cached) and
  * replayed with one launch; chunks < 0 queues |chunks| pieces directly on the streams instead.
  * Device staging buffers are allocated on first use.  Starts after the work queued on `stream` and returns
  * when the host buffers are complete (synchronises `stream`).  b->action is used as the SoA scratch. */
 MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host,
                                  void* obs_host, void* reward_host, uint8_t* done_host, int chunks, mvrl_stream_t stream);
+
+/* Number of pieces mvrl_rov6_step_host cuts a batch of n environments into for a given `chunks` argument
+ * (each piece costs 3 kernel launches, 1 upload and 1-3 downloads). */
+MVRL_API int mvrl_host_chunk_count(int64_t n, int chunks);
 
 /* reset(): mask nullable (= all).  initial_setpoint: 6 host doubles or NULL for
  * the random branch (path and target orientation drawn from Philox). */

@@ -97,6 +97,7 @@ PROTOTYPES = {
     "mvrl_rov6_derivs": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvrl_rov6_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp]),
     "mvrl_rov6_step_range": (_int, [_vp, _i64, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp]),
+    "mvrl_host_chunk_count": (_int, [_i64, _int]),
     "mvrl_rov6_step_host": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp, _vp, _vp, _vp, _int, _vp]),
     "mvrl_rov6_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp, C.POINTER(_d), _vp]),
     "mvrl_rov6_pid": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

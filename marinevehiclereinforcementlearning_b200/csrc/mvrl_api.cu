@@ -374,8 +374,13 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(long n, long ld, const 
     }
 }
 
+// reward_map / done_map (nullable): device aliases of PINNED host arrays.  The block also forwards its 256 rewards
+// and done flags straight to the host (posted PCIe writes, 5 B per environment) so that the download engine has ONE
+// copy per piece to do instead of three - each queued copy costs it ~4.5 us (r1k measurements: 13-15 us per piece).
 template <typename T, int K>
-__global__ void __launch_bounds__(256) soa_to_aos_kernel(long n, long ld, const T* __restrict__ soa, T* __restrict__ aos) {
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(long n, long ld, const T* __restrict__ soa, T* __restrict__ aos,
+                                                         const T* __restrict__ reward, const uint8_t* __restrict__ done,
+                                                         T* __restrict__ reward_map, uint8_t* __restrict__ done_map) {
     constexpr int KP = K | 1;
     __shared__ T tile[256 * KP];
     const long base = (long)blockIdx.x * 256;
@@ -383,6 +388,8 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(long n, long ld, const 
     if ((int)threadIdx.x < cnt) {
 #pragma unroll
         for (int k = 0; k < K; ++k) tile[threadIdx.x * KP + k] = soa[k * ld + base + threadIdx.x];
+        if (reward_map != nullptr) reward_map[base + threadIdx.x] = reward[base + threadIdx.x];
+        if (done_map != nullptr) done_map[base + threadIdx.x] = done[base + threadIdx.x];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < cnt * K; e += 256) aos[base * K + e] = tile[(e / K) * KP + (e % K)];
@@ -429,18 +436,55 @@ static void drop_host_graphs(MvrlRov6* h) {
     }
 }
 
+// Piece boundaries of the host pipeline: `chunks` equal pieces (0: kDefaultChunks), multiples of the 256-environment
+// transpose tile.  Measured on B200 / PCIe gen5 (r1o, r1p): 4 pieces 0.90e9, 6 0.99e9, 8 1.02e9, 12 1.01e9, 16 0.95e9
+// env-steps/s; geometric ramps (small first piece, growing later ones) were all slower than 8 equal pieces.
+static constexpr int kDefaultChunks = 8;
+static int host_chunk_plan(int64_t n, int chunks, int64_t* first /* [kMaxChunks + 1] */) {
+    if (chunks <= 0) chunks = kDefaultChunks;
+    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;
+    int c = 0;
+    first[0] = 0;
+    while (first[c] < n && c < MvrlRov6::kMaxChunks) { first[c + 1] = (first[c] + per < n) ? first[c] + per : n; ++c; }
+    first[c] = n;
+    return c;
+}
+
+extern "C" MVRL_API int mvrl_host_chunk_count(int64_t n, int chunks) {
+    if (n <= 0) return 0;
+    int64_t bounds[MvrlRov6::kMaxChunks + 1];
+    if (chunks < 0) chunks = -chunks;
+    if (chunks > MvrlRov6::kMaxChunks) chunks = MvrlRov6::kMaxChunks;
+    return host_chunk_plan(n, chunks, bounds);
+}
+
+// device-side alias of a pinned host allocation, or null (pageable memory, null pointer, MVRL_HOST_NO_MAP=1)
+static void* mapped_alias(void* host) {
+    if (!host) return nullptr;
+    static const bool off = [] { const char* e = getenv("MVRL_HOST_NO_MAP"); return e && e[0] == '1'; }();
+    if (off) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    return at.devicePointer;
+}
+
 // queues the chunked pipeline: everything is ordered after `root` and joined back into `root`
 static int enqueue_host_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host, void* obs_host,
                              void* reward_host, uint8_t* done_host, int chunks, cudaStream_t root) {
     const size_t es = h->c.dtype == MVRL_F64 ? 8 : 4;
     const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;
-    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;   // multiple of the transpose tile
+    int64_t bounds[MvrlRov6::kMaxChunks + 1];
+    const int n_chunks = host_chunk_plan(n, chunks, bounds);
+    // reward / done: written by the transpose kernel through the device alias of the host arrays when they are pinned
+    // (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory); pageable arrays keep the copy-engine path
+    void* reward_map = mapped_alias(reward_host);
+    uint8_t* done_map = (uint8_t*)mapped_alias(done_host);
     MVRL_CUDA(cudaEventRecord(h->ev_in, root));
     for (int i = 0; i < MvrlRov6::kStreams; ++i) MVRL_CUDA(cudaStreamWaitEvent(h->hs[i], h->ev_in, 0));
     cudaStream_t s_up = h->hs[0], s_k = h->hs[1], s_dn = h->hs[2];
-    int c = 0;
-    for (int64_t first = 0; first < n; first += per, ++c) {
-        const int64_t cnt = (n - first) < per ? (n - first) : per;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t first = bounds[c], cnt = bounds[c + 1] - bounds[c];
         char* d_act = (char*)h->stage_act + (size_t)first * n_act * es;
         char* d_obs = (char*)h->stage_obs + (size_t)first * 9 * es;
         MVRL_CUDA(cudaMemcpyAsync(d_act, (const char*)actions_host + (size_t)first * n_act * es, (size_t)cnt * n_act * es, cudaMemcpyHostToDevice, s_up));
@@ -449,13 +493,15 @@ static int enqueue_host_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6B
         if (es == 8) launch_transposes_in<double>(n_act, cnt, ld, (const double*)d_act, (double*)b->action + first, s_k);
         else launch_transposes_in<float>(n_act, cnt, ld, (const float*)d_act, (float*)b->action + first, s_k);
         launch_step_range(h, first, cnt, ld, b, s_k);
-        if (es == 8) soa_to_aos_kernel<double, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const double*)b->obs + first, (double*)d_obs);
-        else soa_to_aos_kernel<float, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const float*)b->obs + first, (float*)d_obs);
+        if (es == 8) soa_to_aos_kernel<double, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const double*)b->obs + first, (double*)d_obs,
+            (const double*)b->reward + first, b->done + first, reward_map ? (double*)reward_map + first : nullptr, done_map ? done_map + first : nullptr);
+        else soa_to_aos_kernel<float, 9><<<grid_for(cnt, 256), 256, 0, s_k>>>(cnt, ld, (const float*)b->obs + first, (float*)d_obs,
+            (const float*)b->reward + first, b->done + first, reward_map ? (float*)reward_map + first : nullptr, done_map ? done_map + first : nullptr);
         MVRL_CUDA(cudaEventRecord(h->ev_k[c], s_k));
         MVRL_CUDA(cudaStreamWaitEvent(s_dn, h->ev_k[c], 0));
         MVRL_CUDA(cudaMemcpyAsync((char*)obs_host + (size_t)first * 9 * es, d_obs, (size_t)cnt * 9 * es, cudaMemcpyDeviceToHost, s_dn));
-        if (reward_host) MVRL_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)first * es, (const char*)b->reward + (size_t)first * es, (size_t)cnt * es, cudaMemcpyDeviceToHost, s_dn));
-        if (done_host) MVRL_CUDA(cudaMemcpyAsync(done_host + first, b->done + first, (size_t)cnt, cudaMemcpyDeviceToHost, s_dn));
+        if (reward_host && !reward_map) MVRL_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)first * es, (const char*)b->reward + (size_t)first * es, (size_t)cnt * es, cudaMemcpyDeviceToHost, s_dn));
+        if (done_host && !done_map) MVRL_CUDA(cudaMemcpyAsync(done_host + first, b->done + first, (size_t)cnt, cudaMemcpyDeviceToHost, s_dn));
     }
     { const int rc = check_launch("rov6_step_host"); if (rc != MVRL_OK) return rc; }
     for (int i = 0; i < MvrlRov6::kStreams; ++i) {
@@ -477,7 +523,6 @@ extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, 
     if (h->stage_act_bytes < need_act || h->stage_obs_bytes < need_obs) drop_host_graphs(h);  // they hold the old staging pointers
     { const int rc = ensure_host_pipeline(h, need_act, need_obs); if (rc != MVRL_OK) return rc; }
     const bool graph_mode = chunks >= 0;   // chunks < 0: |chunks| pieces queued directly on the streams (no graph)
-    if (chunks == 0) chunks = 4;
     if (chunks < 0) chunks = -chunks;
     if (chunks > MvrlRov6::kMaxChunks) chunks = MvrlRov6::kMaxChunks;
     cudaStream_t user = (cudaStream_t)stream;

@@ -336,13 +336,13 @@ class _RovVecEnv:
             infos["terminal_observation"] = self._terminal_obs[:, :n].T
         return self.state, self._reward[:n], self._done[:n].bool(), infos
 
-    def step_host(self, actions, obs_out=None, reward_out=None, done_out=None, chunks=4):
+    def step_host(self, actions, obs_out=None, reward_out=None, done_out=None, chunks=0):
         """One env step for a caller that lives on the HOST: ``actions`` is a CPU tensor
         ``[N, A]`` (pinned memory lets the copies overlap), results land in CPU tensors
         ``obs [N, obs]``, ``reward [N]``, ``done [N]`` (uint8), allocated pinned on first use.
         Runs ``mvrl_rov6_step_host``: upload, SoA transpose, fused step, transpose back and
-        download are pipelined over ``chunks`` pieces of the batch.  Returns when the host
-        tensors are complete."""
+        download are pipelined over ``chunks`` equal pieces of the batch (0: the library's
+        default).  Returns when the host tensors are complete."""
         if self.HANDLE.PREFIX != "mvrl_rov6":
             raise NotImplementedError("step_host / step_range are implemented for the 6DoF env")
         n = self.num_envs

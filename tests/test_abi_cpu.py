@@ -96,3 +96,13 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"oracle", src, re.I), os.path.join(dirpath, f)
+
+
+def test_host_chunk_plan(lib):
+    """Host logic of mvrl_rov6_step_host's piece schedule (no GPU needed)."""
+    assert lib.mvrl_host_chunk_count(0, 0) == 0
+    assert lib.mvrl_host_chunk_count(1, 0) == 1 and lib.mvrl_host_chunk_count(257, 0) == 2
+    assert lib.mvrl_host_chunk_count(1 << 20, 0) == 8
+    assert lib.mvrl_host_chunk_count(1 << 20, 4) == 4 and lib.mvrl_host_chunk_count(1 << 20, -3) == 3
+    assert lib.mvrl_host_chunk_count(1000, 64) == 4          # pieces are multiples of the 256-env transpose tile
+    assert lib.mvrl_host_chunk_count(1 << 20, 1000) == 64    # capped
