@@ -192,6 +192,12 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     T mm[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) mm[k] = a.mults[k * ld + i];
+    // every remaining input is loaded here, before the first store: the compiler cannot move a load above a store
+    // through pointers it must assume to alias, and a load issued at its point of use is a full DRAM round trip on
+    // the critical path (profiles/ r1t: err_o, ep_return and episode were 25 % of the stall samples)
+    const T err_o0 = a.err_o[i], err_o1 = a.err_o[ld + i], err_o2 = a.err_o[2 * ld + i];
+    const T ep_return_in = a.ep_return[i];
+    const uint32_t episode_in = a.auto_reset ? a.episode[i] : 0u;
     bool is_done = istep >= a.max_steps;
 
     // recentActions.appendleft(action): ring slot, then statistics over the valid entries
@@ -237,7 +243,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     r = r + ar * a.dt;
 
     T obs[11];
-    observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, a.err_o[i], a.err_o[ld + i], a.err_o[2 * ld + i], obs);
+    observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, err_o0, err_o1, err_o2, obs);
 
     T bonus = T(0);
     if (x < P.xmin || x > P.xmax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
@@ -270,7 +276,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     const T t2 = Real<T>::exp(T(-0.6) * rms);
     const T t3 = T(-0.1) * (a0 * a0 + a1 * a1 + a2 * a2) / T(3);
     const T rew = t0 + t1 + t2 + t3 + bonus;
-    const T ep_ret = a.ep_return[i] + rew;
+    const T ep_ret = ep_return_in + rew;
 
     if (a.aux != nullptr) {  // the per-step log columns of verySimpleAuv.py:389-401 that are not state/obs
         const T vals[14] = {Fx, Fy, fh2, Fx_set, Fy_set, N_set, cur[0], cur[1], rms, t0, t1, t2, t3, bonus};
@@ -287,7 +293,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
 #pragma unroll
             for (int k = 0; k < 11; ++k) a.term_obs[k * ld + i] = obs[k];
         }
-        const uint32_t ep = a.episode[i] + 1u;
+        const uint32_t ep = episode_in + 1u;
         a.episode[i] = ep;
         draw_reset_auv(P, a.seed, a.env_id0 + (unsigned long long)i, ep, a.apply_noise != 0, mm, &x, &y, &psi, &heading_target, &t_offset);
 #pragma unroll
