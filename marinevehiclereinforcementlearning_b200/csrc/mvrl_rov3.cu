@@ -87,7 +87,7 @@ static int step3_impl(const MvrlRov3* h, const Rov3Dev<T>& P, int64_t n, int64_t
     a.state = (T*)b->state; a.action = (const T*)b->action; a.obs = (T*)b->obs; a.reward = (T*)b->reward; a.done = b->done;
     a.istep = b->istep; a.setpoint = (T*)b->setpoint; a.path = (T*)b->path; a.ctrl = (T*)b->ctrl; a.episode = b->episode;
     a.term_obs = (T*)b->terminal_obs; a.aux = (T*)b->aux; a.stats = b->ep_stats;
-    a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub); a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
+    a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub); a.hh = T(0.5) * a.h; a.h6 = a.h / T(6); a.h3 = a.h / T(3); a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0; a.auto_reset = h->c.auto_reset; a.fixed_sp = h->c.fixed_sp;
     const unsigned g = mvrl_grid_for(n, 128);
     constexpr bool F32 = sizeof(T) == 4;

@@ -99,7 +99,7 @@ template <typename T> struct Rov3StepArgs {
     long n, ld;
     T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
     T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
-    T dt, h;
+    T dt, h, hh, h6, h3;   // host-computed step sizes (uniform-register operands, see Rov6StepArgs)
     int n_sub, max_steps;
     unsigned long long seed, env_id0;
     int auto_reset, fixed_sp;
@@ -177,7 +177,7 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
     };
     // RK4 as in rov6_step_kernel: fp32 pose advanced by the summed increment with a Kahan carry
     constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
-    const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6), h3 = a.h / T(3);
+    const T h = a.h, hh = a.hh, h6 = a.h6, h3 = a.h3;
     T carry[3] = {T(0), T(0), T(0)};
     for (int sub = 0; sub < a.n_sub; ++sub) {
         T k[6], acc[6], yt[6];

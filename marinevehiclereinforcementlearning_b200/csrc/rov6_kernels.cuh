@@ -14,7 +14,9 @@ template <typename T> struct Rov6StepArgs {
     long n, ld;
     T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
     T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
-    T dt, h;
+    T dt, h, hh, h6, h3;   // env step, RK4 step h = dt / n_sub and h/2, h/6, h/3 - computed on the host: kernel arguments reach the
+                           // FMAs through uniform registers, whereas a value computed in the kernel occupies a vector register and
+                           // makes every y + c k update an FMA with three register sources (3 instead of 2 pipe cycles as FFMA2)
     int n_sub, max_steps;
     unsigned long long seed, env_id0;
     int auto_reset, fixed_sp;
@@ -309,7 +311,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     // a small known offset, and use the addition theorem (sincos_delta) unless the offset is large.
     constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
     constexpr bool ANCHOR = (sizeof(T) == 4) && !FAST && (MVRL_TRIG_ANCHOR != 0);
-    const T h = a.h, hh = T(0.5) * a.h, h6 = a.h / T(6), h3 = a.h / T(3);
+    const T h = a.h, hh = a.hh, h6 = a.h6, h3 = a.h3;
     V carry[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) carry[j] = V(T(0));
