@@ -313,6 +313,8 @@ static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t first
     a.episode = b->episode ? b->episode + first : nullptr; a.term_obs = off(b->terminal_obs); a.aux = off(b->aux); a.stats = b->ep_stats;
     a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub);
     a.hh = T(0.5) * a.h; a.h6 = a.h / T(6); a.h3 = a.h / T(3);   // in T arithmetic, like the kernel used to
+    const T dtc[2] = {T(0), a.hh};
+    for (int i = 0; i < 2; ++i) { a.pid_inv_dt[i] = T(1) / (dtc[i] > T(1e-9) ? dtc[i] : T(1e-9)); a.pid_half_dt[i] = T(0.5) * dtc[i]; }
     a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0 + (unsigned long long)first;
     a.auto_reset = h->c.auto_reset; a.fixed_sp = h->c.fixed_sp;

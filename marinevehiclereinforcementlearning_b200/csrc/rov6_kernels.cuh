@@ -14,6 +14,7 @@ template <typename T> struct Rov6StepArgs {
     long n, ld;
     T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
     T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
+    T pid_inv_dt[2], pid_half_dt[2];   // 1 / max(1e-9, dtc) and dtc / 2 of the PID for dtc = 0 and dtc = h/2 (host-computed, see h6)
     T dt, h, hh, h6, h3;   // env step, RK4 step h = dt / n_sub and h/2, h/6, h/3 - computed on the host: kernel arguments reach the
                            // FMAs through uniform registers, whereas a value computed in the kernel occupies a vector register and
                            // makes every y + c k update an FMA with three register sources (3 instead of 2 pipe cycles as FFMA2)
@@ -268,6 +269,11 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         for (int k = 3; k < 6; ++k) sp[k] = load_v<V>(a.setpoint + k * ld, i0, pair);
     }
 
+    if constexpr (MODE == ACT_SETPOINT) {
+        const V pose0[6] = {y[0], y[1], y[2], y[3], y[4], y[5]};
+        pid6_prime(e_old, sp, pose0);
+    }
+
     V H[6];       // thruster wrench of the current evaluation
     V gcf[6];     // generalisedControlForces of the last evaluation
     V dem[8];     // allocated demand (N) of the last evaluation
@@ -281,13 +287,13 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         for (int k = 0; k < 6; ++k) gcf[k] = act[k];
     }
 
-    // one derivative evaluation; dtc = t - tOld of the PID (0 or h/2 inside a step)
-    auto f = [&](const Trig6<V>& g, const V (&s)[12], V (&k)[12], T dtc) {
+    // one derivative evaluation; half = 1 where t - tOld of the PID is h/2, 0 where it is 0 (the only two values inside a step)
+    auto f = [&](const Trig6<V>& g, const V (&s)[12], V (&k)[12], int half) {
         const V nu[6] = {s[6], s[7], s[8], s[9], s[10], s[11]};
         if constexpr (MODE != ACT_RPM) {
             if constexpr (MODE == ACT_SETPOINT) {
                 const V pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
-                pid6(P, e_old, e_int, sp, pose, dtc, gcf);
+                pid6_core<false>(P, e_old, e_int, sp, pose, a.pid_inv_dt[half], a.pid_half_dt[half], gcf);
             }
             allocate_demand<V, SP>(P, g, gcf, dem);
             V F[8];
@@ -347,7 +353,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
             } else {
                 g = trig6<V, FAST>(yt[3], yt[4], yt[5]);
             }
-            f(g, yt, k, (st & 1) ? hh : T(0));
+            f(g, yt, k, st & 1);
             const T wk = (st == 0 || st == 3) ? h6 : h3;
             const T ck = (st == 2) ? h : hh;
 #pragma unroll

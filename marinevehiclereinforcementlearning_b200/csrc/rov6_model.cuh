@@ -403,27 +403,53 @@ __device__ __forceinline__ void kinematics6(const Trig6<V>& g, const V (&nu)[6],
     ed[4] = fmaf_t(g.cph, q, -(g.sph * r));
 }
 
+// controller error of BlueROV2Heavy6DoF_PID_controller.computeControlForces (6DoF.py:55-61):
+// roll / pitch errors are raw differences, only yaw is wrapped
+template <typename V> __device__ __forceinline__ void pid6_error(const V (&sp)[6], const V (&pose)[6], V (&e)[6]) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) e[k] = sp[k] - pose[k];
+    e[5] = angle_error(sp[5], pose[5]);
+}
+
 // BlueROV2Heavy6DoF_PID_controller.computeControlForces, 6DoF.py:43-73.
 // dtc = t - tOld (the same for every environment of a thread).  e_old[0] = NaN encodes eOld is None.
-template <typename V, typename S>
-__device__ __forceinline__ void pid6(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_int)[6], const V (&sp)[6],
-                                     const V (&pose)[6], S dtc, V (&out)[6]) {
+// CHECK_NONE = false: the caller has already replaced a None eOld by the error of the first call (pid6_prime),
+// which is what 6DoF.py:62-63 does - saves 13 selects per call inside the RK4 loop of the step kernel.
+// inv_dt = 1 / max(1e-9, dtc) and half_dt = dtc / 2 are passed in: the step kernel gets them from the host
+// (uniform registers), pid6() below derives them from a per-environment dtc.
+template <bool CHECK_NONE = true, typename V, typename S>
+__device__ __forceinline__ void pid6_core(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_int)[6], const V (&sp)[6],
+                                          const V (&pose)[6], S inv_dt, S half_dt, V (&out)[6]) {
     V e[6];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) e[k] = sp[k] - pose[k];   // roll/pitch: raw differences (6DoF.py:59-60)
-    e[5] = angle_error(sp[5], pose[5]);
+    pid6_error(sp, pose, e);
     const auto none = visnan(e_old[0]);
-    const S inv_dt = S(1) / tmax(S(1e-9), dtc);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const V eo = vsel(none, e[k], e_old[k]);
+        const V eo = CHECK_NONE ? vsel(none, e[k], e_old[k]) : e_old[k];
         const V dedt = (e[k] - eo) * V(inv_dt);
-        V ei = fmaf_t(V(S(0.5) * dtc), eo + e[k], e_int[k]);
+        V ei = fmaf_t(V(half_dt), eo + e[k], e_int[k]);
         ei = vsel(vgt(tabs(e[k]), V(P.pWind[k])), V(S(0)), ei);
         const V cvl = fmaf_t(V(P.pKi[k]), ei, fmaf_t(V(P.pKd[k]), dedt, V(P.pKp[k]) * e[k]));
         out[k] = tmax(V(-P.pMax[k]), tmin(V(P.pMax[k]), cvl));
         e_int[k] = ei;
         e_old[k] = e[k];
+    }
+}
+
+template <typename V, typename S>
+__device__ __forceinline__ void pid6(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_int)[6], const V (&sp)[6],
+                                     const V (&pose)[6], S dtc, V (&out)[6]) {
+    pid6_core<true>(P, e_old, e_int, sp, pose, S(1) / tmax(S(1e-9), dtc), S(0.5) * dtc, out);
+}
+
+// eOld of a fresh controller := the error its first call will see (pose = the state at the start of the env step)
+template <typename V> __device__ __forceinline__ void pid6_prime(V (&e_old)[6], const V (&sp)[6], const V (&pose)[6]) {
+    const auto none = visnan(e_old[0]);
+    if (vany(none)) {
+        V e[6];
+        pid6_error(sp, pose, e);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) e_old[k] = vsel(none, e[k], e_old[k]);
     }
 }
 
