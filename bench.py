@@ -40,7 +40,7 @@ MAX_STEPS = 250
 FLOP_PER_ENV_STEP = 1600 * N_SUB + 60          # FMA = 2, other fp ops = 1, libm calls not counted
 BYTES_PER_ENV_STEP_F32 = 177                   # state r/w, action r, obs/reward/done w, counter r/w
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-NCU_TRAFFIC_BYTES = 178.6e6                    # measured DRAM bytes of one 1 Mi-env launch (profiles/r1_s_rov6_step_ncu_full_summary.txt)
+NCU_TRAFFIC_BYTES = 177.4e6                    # measured DRAM bytes of one 1 Mi-env launch (profiles/r1_z_rov6_step_ncu_full_summary.txt)
 
 
 ACTION_SCALE = {"rpm": 3500.0, "force": 40.0, "setpoint": 1.0}
@@ -302,7 +302,7 @@ def run_ours(args, rank, local_rank, world):
         fp_peak = fp64_peak if args.dtype == "f64" else fp32_peak
         roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tflops, "peak": fp_peak, "unit": "TFLOP/s",
                     "frac": ach_tflops / fp_peak, "traffic": NCU_TRAFFIC_BYTES if (mode, args.dtype, n_sub, n) == ("rpm", "f32", N_SUB, ENVS_PER_GPU) else None,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rov6_step launch, ncu --set full, profiles/r1_s_rov6_step_ncu_full_summary.txt",
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rov6_step launch, ncu --set full, profiles/r1_z_rov6_step_ncu_full_summary.txt",
                     "peak_source": "FMA-chain microbenchmark (mvrl_measure_fma_peak: operands from uniform registers) run on this GPU in this "
                     "process; nominal fp32 %.1f. With three distinct register operands FFMA sustains only 0.61 inst/clk/SMSP "
                     "(45.7 TFLOP/s, tools/ffma_regs.cu)" % NOMINAL_FP32_TFLOPS,
