@@ -66,6 +66,28 @@ def workload_name(envs, mode="rpm", dtype="f32", n_sub=N_SUB):
 
 
 # --------------------------------------------------------------------------
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# collective), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, text)
+    else:
+        os.write(_REAL_STDOUT, text)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -186,7 +208,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -329,7 +351,7 @@ def run_ours(args, rank, local_rank, world):
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
                                 "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, reward + done stored into the pinned host arrays by the transpose kernel)"},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -423,7 +445,7 @@ def run_auv(args, rank, local_rank, world):
                              "frac": rate * nbytes / 1e9 / peaks["hbm_gbs"], "traffic": None, "bytes_per_env_step": nbytes,
                              "gathered_bytes_per_env_step_from_l2": 64, "peak_source": peak_src},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -460,7 +482,7 @@ def run_rov3(args, rank, local_rank, world):
                 "config": {"workload": "rov3_step fp32: BlueROV2 Heavy 3DoF, %d envs/GPU, %s actions, dt=%.1f as nSub=%d RK4, maxSteps=%d auto-reset"
                                        % (n, mode, DT, args.n_sub, MAX_STEPS)},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -547,7 +569,7 @@ def run_rollout(args, rank, local_rank, world):
                                        "nSub=%d, CUDA-graph replay, stats all-reduce per rollout" % (n, T, args.n_sub)},
                 "flop_per_env_step": {"env": flop_env, "policy": flop_policy},
                 "gpu_launches": rollouts * T, "clocks": clocks, "episode_stats": stats_holder.get("s")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -579,6 +601,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "rov3":

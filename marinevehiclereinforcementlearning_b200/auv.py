@@ -149,7 +149,7 @@ class AuvVecEnv:
         self.noiseMagCoeffs, self.noiseMagActuation = float(noiseMagCoeffs), float(noiseMagActuation)
         self.lenAction, self.lenObs = self.ACT_DIM, self.OBS_DIM
         n = self.num_envs
-        self.ld = ((n + 31) // 32) * 32
+        self.ld = max(32, ((n + 31) // 32) * 32)    # an empty batch still owns (non-null) buffers
         ld, dev = self.ld, self.device
         z = lambda k: torch.zeros((k, ld), dtype=dtype, device=dev)
         self._state, self._action, self._obs = z(6), z(3), z(11)

@@ -517,8 +517,8 @@ static int enqueue_host_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6B
 extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, const void* actions_host,
                                             void* obs_host, void* reward_host, uint8_t* done_host, int chunks, mvrl_stream_t stream) {
     { const int rc = check_step_args(h, 0, n, ld, b, "mvrl_rov6_step_host"); if (rc != MVRL_OK) return rc; }
+    if (n == 0) return MVRL_OK;   // an empty batch has no host arrays to name
     if (!actions_host || !obs_host) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step_host: actions_host and obs_host are required");
-    if (n == 0) return MVRL_OK;
     MVRL_CUDA(cudaSetDevice(h->c.device));
     const size_t es = h->c.dtype == MVRL_F64 ? 8 : 4;
     const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;

@@ -206,7 +206,7 @@ class _RovVecEnv:
         self.lenObs = self.OBS_DIM
         self.fixedSp = False
         n = self.num_envs
-        self.ld = ((n + 31) // 32) * 32
+        self.ld = max(32, ((n + 31) // 32) * 32)    # an empty batch still owns (non-null) buffers
         ld, dev = self.ld, self.device
         z = lambda k: torch.zeros((k, ld), dtype=dtype, device=dev)
         self._state, self._action, self._obs = z(self.STATE_DIM), z(self.lenAction), z(self.OBS_DIM)
