@@ -134,6 +134,30 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and with them its first-touch / pinned allocations) to the CPUs of the NUMA node the
+    GPU hangs off: the e2e leg moves 76 MB per step between host memory and the GPU, and with one rank per GPU the
+    cross-socket hop otherwise becomes the limiter.  Returns the node, or None when the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -219,6 +243,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if args.bind_numa else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
@@ -347,7 +372,7 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "inputs larger than L2: ~125 MB touched per step + 4 rotating 32 MiB action batches"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "chunks": e2e_pieces, "gpu_launches_per_step": e2e_launches_per_step,
+                        "chunks": e2e_pieces, "host_numa_node": numa_node, "gpu_launches_per_step": e2e_launches_per_step,
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
                                 "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, reward + done stored into the pinned host arrays by the transpose kernel)"},
                 "gpu_launches": args.steps, "clocks": clocks, "episode_stats": stats}
@@ -594,6 +619,7 @@ def main():
     ap.add_argument("--rollout-len", type=int, default=128)
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
     ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
+    ap.add_argument("--bind-numa", type=int, default=1, help="1: bind each rank to the CPUs of its GPU's NUMA node (host buffers of the e2e leg)")
     ap.add_argument("--no-stats", action="store_true", help="diagnostics: do not accumulate episode statistics in the step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
