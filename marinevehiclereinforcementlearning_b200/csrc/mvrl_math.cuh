@@ -187,10 +187,12 @@ __device__ __forceinline__ double warp_max(double v, unsigned mask) {
 // (the CAS loop's leading load was 12 % of the legacy step kernel's stall samples, profiles/ r1t).  NaN is
 // never passed (non-finite environments are counted separately).
 __device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+    v += 0.0;   // -0.0 -> +0.0: its bit pattern would otherwise compare as the most negative integer
     if (v >= 0.0) atomicMin((long long*)addr, __double_as_longlong(v));
     else atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
 __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    v += 0.0;
     if (v >= 0.0) atomicMax((long long*)addr, __double_as_longlong(v));
     else atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
