@@ -128,6 +128,7 @@ struct MvrlRov6 {
     MvrlRov6Params p;
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
+    bool ws;  // warp-specialised persistent step kernel for fp32 / rpm / default sparsity (MVRL_WS=1 in the environment enables it)
     bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
@@ -206,6 +207,8 @@ static bool default_sparsity(const MvrlRov6Params& p) {
     return true;
 }
 
+int mvrl_rov6_ws_prepare(int device);
+
 extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, const MvrlRov6Config* cfg) {
     if (!out || !params || !cfg) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_create: null argument");
     if (cfg->dtype != MVRL_F32 && cfg->dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "dtype must be MVRL_F32 or MVRL_F64");
@@ -220,8 +223,10 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->c = *cfg;
     h->sp = default_sparsity(*params);
     { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
+    { const char* e = getenv("MVRL_WS"); h->ws = (e && e[0] == '1'); }
     to_dev(*params, h->pf);
     to_dev(*params, h->pd);
+    if (cudaSetDevice(cfg->device) == cudaSuccess) mvrl_rov6_ws_prepare(cfg->device);
     *out = h;
     return MVRL_OK;
 }
@@ -280,11 +285,24 @@ template <typename T> static bool x2_layout_ok(const Rov6StepArgs<T>& a) {
     return true;
 }
 
+// Warp-specialised persistent variant, compiled in its own translation unit (mvrl_rov6_ws.cu)
+int mvrl_rov6_ws_prepare(int device);                                                   // shared-memory opt-in; SM count
+void mvrl_rov6_ws_launch(const Rov6StepArgs<float>& a, int device, cudaStream_t s);
+
 template <typename T, int MODE, bool SP, bool FAST>
-static void launch_step(const Rov6StepArgs<T>& a, bool x2, cudaStream_t s) {
+static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
+    const bool x2 = (flags & 1) != 0, ws = (flags & 2) != 0;   // two environments per thread; warp-specialised variant
     // the four RK4 stages are unrolled: measured faster than the rolled loop (r1 profile notes)
     constexpr int UNROLL = MVRL_STAGE_UNROLL(T);
     if constexpr (sizeof(T) == 4) {
+        if constexpr (MODE == ACT_RPM && SP && !FAST) {
+            if (ws && x2 && x2_layout_ok(a) && a.aux == nullptr) {
+                int device = 0;
+                cudaGetDevice(&device);
+                mvrl_rov6_ws_launch(a, device, s);
+                return;
+            }
+        }
         if (x2 && x2_layout_ok(a)) {
             rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for((a.n + 1) / 2, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
             return;
@@ -293,7 +311,7 @@ static void launch_step(const Rov6StepArgs<T>& a, bool x2, cudaStream_t s) {
     rov6_step_kernel<T, MODE, SP, FAST, UNROLL><<<grid_for(a.n, MVRL_STEP_BLOCK), MVRL_STEP_BLOCK, 0, s>>>(a);
 }
 template <typename T, bool FAST>
-static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, bool x2, cudaStream_t s) {
+static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, int x2, cudaStream_t s) {
     switch (mode * 2 + (sp ? 1 : 0)) {
         case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, s); break;
         case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, s); break;
@@ -334,11 +352,12 @@ static int check_step_args(const MvrlRov6* h, int64_t first, int64_t n, int64_t 
 static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, cudaStream_t s) {
     if (h->c.dtype == MVRL_F64) {
         Rov6StepArgs<double> a; fill_step_args(h, h->pd, first, n, ld, b, a);
-        dispatch_step<double, false>(a, h->c.action_mode, h->sp, false, s);
+        dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
-        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, h->x2, s);
-        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, h->x2, s);
+        const int flags = (h->x2 ? 1 : 0) | (h->ws ? 2 : 0);
+        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, s);
+        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, s);
     }
 }
 

@@ -4,6 +4,13 @@
 #include <stdint.h>
 #include <math.h>
 
+// Rare paths (libm fmod, Philox resets) are kept out of line so that they do not bloat the instruction stream every
+// warp fetches.  The warp-specialised kernel's translation unit defines MVRL_NOINLINE as __forceinline__ instead:
+// ptxas cannot allocate registers under setmaxnreg across a call.
+#ifndef MVRL_NOINLINE
+#define MVRL_NOINLINE __noinline__
+#endif
+
 namespace mvrl {
 
 // ---- precision-generic libm wrappers -------------------------------------
@@ -99,7 +106,7 @@ __device__ __forceinline__ F2 vcopysign(F2 mag, F2 sign) { return F2(copysignf(m
 template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) { return a < T(0) ? a + b : (a >= b ? a - b : tabs(a)); }
 // general case, kept out of line: libm's fmod carries a long slow path that would otherwise be
 // inlined at every call site of the step kernels (measured: instruction-fetch stalls in the epilogue)
-template <typename T> __device__ __noinline__ T pymod_general(T a, T b) {
+template <typename T> __device__ MVRL_NOINLINE T pymod_general(T a, T b) {
     T r = Real<T>::fmod(a, b);
     if (r != T(0)) { if (r < T(0)) r += b; }
     else r = T(0);

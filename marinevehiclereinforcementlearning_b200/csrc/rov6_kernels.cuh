@@ -59,7 +59,7 @@ __device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T 
 // the exact angle part (any magnitude), out of line: wrapped angle and clipped, scaled angle error
 template <typename T> struct WrapObs { T wrapped, obs; };   // returned by value: stays in registers
 template <typename T>
-__device__ __noinline__ WrapObs<T> wrap_angle_exact(T inv_ang, T angle, T sp_angle) {
+__device__ MVRL_NOINLINE WrapObs<T> wrap_angle_exact(T inv_ang, T angle, T sp_angle) {
     WrapObs<T> r;
     r.wrapped = pymod_pos(angle, T(MVRL_TWO_PI));
     r.obs = clampt(angle_error(sp_angle, r.wrapped) * inv_ang, T(-1), T(1));
@@ -72,7 +72,7 @@ __device__ __noinline__ WrapObs<T> wrap_angle_exact(T inv_ang, T angle, T sp_ang
 // environment in max_steps, and three Philox blocks would bloat the common path.
 template <typename T> struct Reset6 { T path[6]; T orient[3]; };
 template <typename T>
-__device__ __noinline__ Reset6<T> draw_reset6(unsigned long long seed, unsigned long long env, uint32_t episode) {
+__device__ MVRL_NOINLINE Reset6<T> draw_reset6(unsigned long long seed, unsigned long long env, uint32_t episode) {
     const uint4 a = Philox::draw(seed, env, episode, 0u, 0u);
     const uint4 b = Philox::draw(seed, env, episode, 0u, 1u);
     const uint4 c = Philox::draw(seed, env, episode, 0u, 2u);
@@ -141,7 +141,7 @@ __device__ __forceinline__ void stats_accumulate_counts(double* stats, int n_don
 // the state, draws the next path / target orientation (unless the set-point is fixed), installs a fresh
 // controller and writes the observation of the fresh state.  Out of line: one environment in max_steps takes it.
 template <typename T, int MODE>
-__device__ __noinline__ void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long i) {
+__device__ MVRL_NOINLINE void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long i) {
     const long ld = a.ld;
     const Rov6Dev<T>& P = a.P;
     if (a.term_obs != nullptr) {

@@ -371,3 +371,26 @@ def test_two_envs_per_thread_kernel_matches_one_env_kernel_bitwise(monkeypatch):
                 nn = lambda t: torch.nan_to_num(t, nan=12345.0)   # ctrl[0] = NaN marks a fresh controller
                 assert torch.equal(packed._state, single._state) and torch.equal(nn(packed._ctrl), nn(single._ctrl)), (mode, fast, k)
             assert packed.episode_stats() == single.episode_stats()
+
+
+def test_warp_specialised_kernel_matches_plain_kernel_bitwise(monkeypatch):
+    """The opt-in warp-specialised persistent variant (csrc/rov6_ws_kernel.cuh: IO warps + compute warps handing
+    tiles over through mbarriers, MVRL_WS=1) runs the same arithmetic per environment as the plain fused kernel:
+    bitwise equal observations, dones, states, way-points, counters and statistics, with auto-reset, for batch sizes
+    that leave lanes, warps and whole CTAs of the persistent grid empty."""
+    kw = dict(action_mode="rpm", dtype=torch.float32, device=DEV, maxSteps=3, auto_reset=True, seed=5)
+    for n in (1, 65, 777, 100001):
+        rng = np.random.default_rng(n)
+        acts = torch.as_tensor(rng.uniform(-3500, 3500, (7, n, 8)), dtype=torch.float32, device=DEV)
+        monkeypatch.setenv("MVRL_WS", "0")
+        plain = BlueROV2Heavy6DoFVecEnv(n, **kw)
+        monkeypatch.setenv("MVRL_WS", "1")
+        ws = BlueROV2Heavy6DoFVecEnv(n, **kw)
+        assert torch.equal(plain.reset(), ws.reset())
+        for k in range(acts.shape[0]):
+            op, _, dp, ip = plain.step(acts[k])
+            ow, _, dw, iw = ws.step(acts[k])
+            assert torch.equal(op, ow) and torch.equal(dp, dw), (n, k)
+            assert torch.equal(ip["terminal_observation"], iw["terminal_observation"]), (n, k)
+            assert torch.equal(plain._state, ws._state) and torch.equal(plain._path, ws._path) and torch.equal(plain._istep, ws._istep), (n, k)
+        assert plain.episode_stats() == ws.episode_stats()
