@@ -164,7 +164,7 @@ MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t
 /* One env step with HOST buffers - the call a host-side VecEnv user makes (BlueROV2Heavy6DoFEnv.step for n
  * vehicles, 6DoF.py:531-594): actions_host T [n][A] (row = environment) in; obs_host T [n][9], reward_host
  * T [n] (nullable), done_host [n] (nullable) out.  Pinned host memory is needed for the copies to overlap.
- * The batch is cut into `chunks` equal pieces (0: the default, 8); upload, transpose to SoA, fused step, transpose
+ * The batch is cut into `chunks` equal pieces (0: the default - 8, fewer for batches under 512 Ki environments); upload, transpose to SoA, fused step, transpose
  * back and download of different pieces overlap on streams owned by the handle (PCIe is full duplex).  The
  * observations travel by copy engine; reward and done flags (5 B per environment) are stored straight into
  * reward_host / done_host by the transpose kernel when those arrays are pinned, so that the download engine has

@@ -101,7 +101,8 @@ def test_product_does_not_import_oracle():
 def test_host_chunk_plan(lib):
     """Host logic of mvrl_rov6_step_host's piece schedule (no GPU needed)."""
     assert lib.mvrl_host_chunk_count(0, 0) == 0
-    assert lib.mvrl_host_chunk_count(1, 0) == 1 and lib.mvrl_host_chunk_count(257, 0) == 2
+    assert lib.mvrl_host_chunk_count(1, 0) == 1 and lib.mvrl_host_chunk_count(257, 0) == 1 and lib.mvrl_host_chunk_count(257, 8) == 2
+    assert lib.mvrl_host_chunk_count(4096, 0) == 1 and lib.mvrl_host_chunk_count(1 << 18, 0) == 4   # default: no piece under 64 Ki envs
     assert lib.mvrl_host_chunk_count(1 << 20, 0) == 8
     assert lib.mvrl_host_chunk_count(1 << 20, 4) == 4 and lib.mvrl_host_chunk_count(1 << 20, -3) == 3
     assert lib.mvrl_host_chunk_count(1000, 64) == 4          # pieces are multiples of the 256-env transpose tile
