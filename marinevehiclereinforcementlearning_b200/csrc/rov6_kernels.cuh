@@ -231,20 +231,34 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     const long ld = a.ld;
     constexpr bool EXACT = (sizeof(T) == 8);
 
-    V y[12];
+    // rows of one array are ld elements apart: walk a byte pointer instead of forming base + k * ld + i0 per row.  The second
+    // environment of an unpaired thread (odd batch) reads the row's padding element: rows are padded to an even ld >= n + 1.
+    const long row_bytes = ld * (long)sizeof(T);
+    auto walk = [&](const T* base, V* dst, int rows) {
+        if constexpr (L == 2) {
+            const char* p = reinterpret_cast<const char*>(base + i0);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) y[k] = load_v<V>(a.state + k * ld, i0, pair);
+            for (int k = 0; k < rows; ++k, p += row_bytes) dst[k] = f2_from(*reinterpret_cast<const float2*>(p));
+        } else {   // one environment per thread: indexed rows measured faster (r1_walk)
+#pragma unroll
+            for (int k = 0; k < rows; ++k) dst[k] = base[k * ld + i0];
+        }
+    };
+    V y[12];
+    walk(a.state, y, 12);
 
     constexpr int NA = (MODE == ACT_RPM) ? 8 : 6;
     V act[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) act[k] = load_v<V>(a.action + k * ld, i0, pair);
+    walk(a.action, act, NA);
     // Needed by the epilogue only: the way-points are copied global -> shared with cp.async (LDGSTS) now, so their
     // DRAM latency hides behind the RK4 loop without holding 6 (12) registers across it - as registers they were
     // spilled (r1i profile: STL in the prologue and LDL / long-scoreboard stalls in the epilogue).
     __shared__ V s_path[6][StepLaunch<V>::BLOCK];
+    {
+        const char* p = reinterpret_cast<const char*>(a.path + i0);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) cp_async_v<V>(&s_path[k][threadIdx.x], a.path + k * ld + i0, pair);
+        for (int k = 0; k < 6; ++k, p += row_bytes) cp_async_v<V>(&s_path[k][threadIdx.x], reinterpret_cast<const T*>(p), (L == 2) || pair);
+    }
     int istep_in[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) istep_in[l] = (l == 0 || pair) ? a.istep[i0 + l] : 0;
@@ -453,10 +467,20 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     }
 
     if (a.stats != nullptr) stats_accumulate_counts(a.stats, n_done_t, len_t, n_bad_t);
+    auto walk_out = [&](T* base, const V* src, int rows) {   // same pointer walk for the stores; the unpaired thread stores one element
+        if constexpr (L == 2) {
+            char* p = reinterpret_cast<char*>(base + i0);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) store_v<V>(a.state + k * ld, i0, pair, y[k]);
+            for (int k = 0; k < rows; ++k, p += row_bytes) {
+                if (pair) *reinterpret_cast<float2*>(p) = src[k].v; else *reinterpret_cast<float*>(p) = src[k].v.x;
+            }
+        } else {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) store_v<V>(a.obs + k * ld, i0, pair, obs_v[k]);
+            for (int k = 0; k < rows; ++k) base[k * ld + i0] = src[k];
+        }
+    };
+    walk_out(a.state, y, 12);
+    walk_out(a.obs, obs_v, 9);
     store_v<V>(a.reward, i0, pair, V(T(0)));  // 6DoF.py:575
     if constexpr (MODE == ACT_SETPOINT) {
 #pragma unroll
