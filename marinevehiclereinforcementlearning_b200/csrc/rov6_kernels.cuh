@@ -38,8 +38,10 @@ __device__ __forceinline__ void observe6(const Rov6Dev<T>& P, const T (&y)[12], 
 // angle is inside (-2 pi, 4 pi) and every angle error inside (-2 pi, 2 pi); returns false when that does not
 // hold (the caller then redoes the angle part with the exact, out-of-line functions).  One test at the end
 // instead of a branch per modulo.
+// pos[6] = (path - position) / (3 Length) comes in already scaled (the packed kernel forms it for both of a thread's
+// environments at once with two packed instructions per way-point component)
 template <typename T>
-__device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T (&y)[12], const T (&path)[6], const T (&sp_ang)[3],
+__device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T (&y)[12], const T (&pos)[6], const T (&sp_ang)[3],
                                                    T (&wrapped)[3], T (&obs)[9]) {
     const T tp = T(MVRL_TWO_PI);
     T lo = y[3], hi = y[3], worst = T(0);
@@ -49,8 +51,8 @@ __device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T 
         wrapped[k] = pymod_small(y[3 + k], tp);
         const T d = sp_ang[k] - wrapped[k];
         worst = tmax(worst, tabs(d));
-        obs[k] = clampt((path[k] - y[k]) * P.inv_3L, T(-1), T(1));
-        obs[3 + k] = clampt((path[3 + k] - y[k]) * P.inv_3L, T(-1), T(1));
+        obs[k] = clampt(pos[k], T(-1), T(1));
+        obs[3 + k] = clampt(pos[3 + k], T(-1), T(1));
         obs[6 + k] = clampt(angle_error_small(d) * P.inv_ang, T(-1), T(1));
     }
     return lo > -tp && hi < tp + tp && worst < tp;   // all false for NaN: the exact path then propagates it
@@ -261,7 +263,13 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     }
     int istep_in[L];
 #pragma unroll
-    for (int l = 0; l < L; ++l) istep_in[l] = (l == 0 || pair) ? a.istep[i0 + l] : 0;
+    for (int l = 0; l < L; ++l) istep_in[l] = 0;
+    if constexpr (L == 2) {   // both counters in one 8-byte load (an unpaired thread reads, and ignores, the padding / neighbour)
+        const int2 q = *reinterpret_cast<const int2*>(a.istep + i0);
+        istep_in[0] = q.x; istep_in[L - 1] = q.y;
+    } else {
+        istep_in[0] = a.istep[i0];
+    }
 
     V sp[6];
     V e_old[6], e_int[6];
@@ -394,9 +402,16 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
     V obs_v[9];
+    V pos_v[6];   // (way-point - position) / (3 Length), 6DoF.py:470-476, for every environment of the thread at once
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pos_v[k] = (path_v[k] - y[k]) * V(P.inv_3L);
+        pos_v[3 + k] = (path_v[3 + k] - y[k]) * V(P.inv_3L);
+    }
     int n_done_t = 0, len_t = 0, n_bad_t = 0;
     bool reset_lane[L], lane_on[L], ok[L];
     int istep[L];
+    unsigned char done_flag[L];
     T ang_raw[L][3], spa[L][3];
     // phase A - both environments of the thread in one basic block (no branch in between: the two dependency
     // chains interleave): wrap (6DoF.py:560) and dataToState (467-483) on the fast path
@@ -407,7 +422,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) ys[k] = lane_get(y[k], l);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
+        for (int k = 0; k < 6; ++k) path[k] = lane_get(pos_v[k], l);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { spa[l][k] = lane_get(sp[3 + k], l); ang_raw[l][k] = ys[3 + k]; }
         istep[l] = istep_in[l] + 1;
@@ -425,11 +440,20 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         n_done_t += reset_lane[l] ? 1 : 0;
         len_t += reset_lane[l] ? istep[l] : 0;
         n_bad_t += (lane_on[l] && bad) ? 1 : 0;
-        if (lane_on[l]) {
-            a.done[i0 + l] = is_done ? 1 : 0;
-            a.istep[i0 + l] = istep[l];
-            if constexpr (MODE == ACT_SETPOINT) a.ctrl[12 * ld + i0 + l] = T(istep[l]) * a.dt;
+        done_flag[l] = is_done ? 1 : 0;
+        if constexpr (MODE == ACT_SETPOINT) { if (lane_on[l]) a.ctrl[12 * ld + i0 + l] = T(istep[l]) * a.dt; }
+    }
+    if constexpr (L == 2) {   // done flags and counters of a paired thread go out as one 2-byte and one 8-byte store
+        if (pair) {
+            *reinterpret_cast<uchar2*>(a.done + i0) = make_uchar2(done_flag[0], done_flag[L - 1]);
+            *reinterpret_cast<int2*>(a.istep + i0) = make_int2(istep[0], istep[L - 1]);
+        } else {
+            a.done[i0] = done_flag[0];
+            a.istep[i0] = istep[0];
         }
+    } else {
+        a.done[i0] = done_flag[0];
+        a.istep[i0] = istep[0];
     }
     // phase B - rare: an angle outside the fast range goes through the exact, out-of-line modulo
     bool all_ok = true;

@@ -141,6 +141,12 @@ __device__ __forceinline__ int ws_observe(const Rov6StepArgs<float>& a, bool pai
     for (int k = 0; k < 12; ++k) nonfinite = fmaf_t(y[k], V(T(0)), nonfinite);
     bool lane_on[L], ok[L];
     T ang_raw[L][3], spa[L][3];
+    V pos_v[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pos_v[k] = (path_v[k] - y[k]) * V(P.inv_3L);
+        pos_v[3 + k] = (path_v[3 + k] - y[k]) * V(P.inv_3L);
+    }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         lane_on[l] = (l == 0) || pair;
@@ -148,7 +154,7 @@ __device__ __forceinline__ int ws_observe(const Rov6StepArgs<float>& a, bool pai
 #pragma unroll
         for (int k = 0; k < 12; ++k) ys[k] = lane_get(y[k], l);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) path[k] = lane_get(path_v[k], l);
+        for (int k = 0; k < 6; ++k) path[k] = lane_get(pos_v[k], l);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { spa[l][k] = lane_get(sp_ang[k], l); ang_raw[l][k] = ys[3 + k]; }
         istep[l] = istep[l] + 1;
