@@ -40,7 +40,7 @@ MAX_STEPS = 250
 FLOP_PER_ENV_STEP = 1600 * N_SUB + 60          # FMA = 2, other fp ops = 1, libm calls not counted
 BYTES_PER_ENV_STEP_F32 = 177                   # state r/w, action r, obs/reward/done w, counter r/w
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-NCU_TRAFFIC_BYTES = 177.4e6                    # measured DRAM bytes of one 1 Mi-env launch (profiles/r1_z_rov6_step_ncu_full_summary.txt)
+NCU_TRAFFIC_BYTES = 176.3e6                    # measured DRAM bytes of one 1 Mi-env launch (profiles/r1_z_rov6_step_ncu_full_summary.txt)
 
 
 ACTION_SCALE = {"rpm": 3500.0, "force": 40.0, "setpoint": 1.0}

@@ -103,8 +103,12 @@ __device__ __forceinline__ F2 vcopysign(F2 mag, F2 sign) { return F2(copysignf(m
 // angles with it (dynamicsModel_BlueROV2_Heavy_6DoF.py:560, resources.py:92-93).
 // -b < a < 2b (the overwhelmingly common case: an angle wrapped one step ago, moved by less than a turn):
 // no fmod, no branch.  a - b is exact for b <= a < 2b (Sterbenz), which is what fmod returns there.
-template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) {
-    const T shift = a < T(0) ? b : (a >= b ? -b : T(0));   // a + 0 == |a| on [0, b) and turns -0 into +0, like the reference's %
+template <typename T> __device__ __forceinline__ T pymod_small(T a, T b) { return a < T(0) ? a + b : (a >= b ? a - b : tabs(a)); }
+// the same value from one add of a selected shift: a + 0 == |a| on [0, b) and turns -0 into +0 like the reference's %.  Straight-line
+// code for the 6DoF step kernel's two-environment epilogue (+0.6 %); the legacy step kernel is 21 % SLOWER with it (the compiler
+// schedules its loads differently around the selects, measured r1_auvab), so it keeps the form above.
+template <typename T> __device__ __forceinline__ T pymod_small_sel(T a, T b) {
+    const T shift = a < T(0) ? b : (a >= b ? -b : T(0));
     return a + shift;
 }
 // general case, kept out of line: libm's fmod carries a long slow path that would otherwise be

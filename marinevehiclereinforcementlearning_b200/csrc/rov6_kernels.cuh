@@ -48,7 +48,7 @@ __device__ __forceinline__ bool wrap_observe6_fast(const Rov6Dev<T>& P, const T 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         lo = tmin(lo, y[3 + k]); hi = tmax(hi, y[3 + k]);
-        wrapped[k] = pymod_small(y[3 + k], tp);
+        wrapped[k] = pymod_small_sel(y[3 + k], tp);
         const T d = sp_ang[k] - wrapped[k];
         worst = tmax(worst, tabs(d));
         obs[k] = clampt(pos[k], T(-1), T(1));
