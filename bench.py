@@ -354,6 +354,11 @@ def run_ours(args, rank, local_rank, world):
                     "process; nominal fp32 %.1f. With three distinct register operands FFMA sustains only 0.61 inst/clk/SMSP "
                     "(45.7 TFLOP/s, tools/ffma_regs.cu)" % NOMINAL_FP32_TFLOPS,
                     "fp32_peak_tflops": fp32_peak, "fp64_peak_tflops": fp64_peak, "flop_per_env_step": flop,
+                    # what the shipped kernel actually executes (packed FFMA2 = 2 FMA; counted from its SASS with
+                    # tools/sass_operands.py: 365 FFMA2 + 158 FMUL2 + 37 FADD2 + 16 scalar per sub-step and pair of environments):
+                    # folding / hoisting / anchored trig make it fewer flops than the frozen algorithmic count, hence frac ~ 1
+                    "executed_flop_per_env_step": (933 * n_sub + 100) if (mode, args.dtype) == ("rpm", "f32") else None,
+                    "executed_frac": (per_gpu_rate * (933 * n_sub + 100) / 1e12 / fp_peak) if (mode, args.dtype) == ("rpm", "f32") else None,
                     "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                             "bytes_per_env_step": nbytes, "peak_source": peak_src}}
         cpu = None
