@@ -62,7 +62,9 @@ __device__ __forceinline__ void flow_interp(const FlowDev<T>& f, T time, T x, T 
 #ifndef MVRL_AUV_STAGE_SMEM
 #define MVRL_AUV_STAGE_SMEM 1
 #endif
-#define MVRL_AUV_BLOCK 128
+#ifndef MVRL_AUV_BLOCK
+#define MVRL_AUV_BLOCK 128   // measured: 64 threads per block +1 % (noise level), 256 threads -18 % (r1_auvblk)
+#endif
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
