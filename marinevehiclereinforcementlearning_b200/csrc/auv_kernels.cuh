@@ -186,31 +186,32 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     T tx = T(0), ty = T(0);   // positionTarget: the origin, or the current way-point of AuvEnvCyl
     if (P.cyl) { iwp = a.iwp[i]; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
     const int istep = a.istep[i] + 1;
-    const T time = T(istep) * a.dt;
-    const FlowCell<T> cell = flow_locate(a.flow, time + t_offset, x, y);
-    if constexpr (STAGE) flow_stage_issue(a.flow, cell, stage);   // in flight while the rest of the inputs arrive
+    // EVERY input is requested here, before anything waits on one of them and before the first store: the flow-cell
+    // lookup below stalls on x / y / istep, and whatever is issued after it pays a second DRAM round trip; the compiler
+    // cannot move a load above a store through pointers it must assume to alias (profiles/ r1t: err_o, ep_return and
+    // episode, loaded at their point of use, were 25 % of the stall samples)
     T u = a.state[3 * ld + i], v = a.state[4 * ld + i], r = a.state[5 * ld + i];
     const T a0 = a.action[i], a1 = a.action[ld + i], a2 = a.action[2 * ld + i];
     T mm[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) mm[k] = a.mults[k * ld + i];
-    // every remaining input is loaded here, before the first store: the compiler cannot move a load above a store
-    // through pointers it must assume to alias, and a load issued at its point of use is a full DRAM round trip on
-    // the critical path (profiles/ r1t: err_o, ep_return and episode were 25 % of the stall samples)
     const T err_o0 = a.err_o[i], err_o1 = a.err_o[ld + i], err_o2 = a.err_o[2 * ld + i];
     const T ep_return_in = a.ep_return[i];
     const uint32_t episode_in = a.auto_reset ? a.episode[i] : 0u;
-    bool is_done = istep >= a.max_steps;
-
-    // recentActions.appendleft(action): ring slot, then statistics over the valid entries
-    const int slot = (istep - 1) % 10;
-    const int cnt = istep < 10 ? istep : 10;
     T ring[10][3];
 #pragma unroll
     for (int s = 0; s < 10; ++s) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) ring[s][c] = a.recent[(s * 3 + c) * ld + i];
     }
+    const T time = T(istep) * a.dt;
+    const FlowCell<T> cell = flow_locate(a.flow, time + t_offset, x, y);
+    if constexpr (STAGE) flow_stage_issue(a.flow, cell, stage);   // the gather (L2) lands while the ring statistics below are set up
+    bool is_done = istep >= a.max_steps;
+
+    // recentActions.appendleft(action): ring slot, then statistics over the valid entries
+    const int slot = (istep - 1) % 10;
+    const int cnt = istep < 10 ? istep : 10;
 #pragma unroll
     for (int s = 0; s < 10; ++s) {
         if (s == slot) { ring[s][0] = a0; ring[s][1] = a1; ring[s][2] = a2; }
