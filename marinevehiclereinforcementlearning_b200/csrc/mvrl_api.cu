@@ -280,7 +280,7 @@ int mvrl_require_device(int device) {
 // Two fp32 environments per thread (packed FFMA2 path) need 8-byte aligned rows.
 template <typename T> static bool x2_layout_ok(const Rov6StepArgs<T>& a) {
     if (sizeof(T) != 4 || (a.ld & 1)) return false;
-    const void* ptrs[] = {a.state, a.action, a.obs, a.reward, a.setpoint, a.path, a.ctrl, a.istep};
+    const void* ptrs[] = {a.state, a.action, a.obs, a.reward, a.setpoint, a.path, a.ctrl, a.istep, a.episode};
     for (const void* p : ptrs) if (((uintptr_t)p) & 7u) return false;
     if (((uintptr_t)a.done) & 1u) return false;   // the two done flags of a thread go out as one 2-byte store
     return true;

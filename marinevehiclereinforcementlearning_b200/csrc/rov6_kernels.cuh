@@ -142,15 +142,16 @@ __device__ __forceinline__ void stats_accumulate_counts(double* stats, int n_don
 // the step kernel after its regular stores: keeps the terminal observation, bumps the episode counter, zeroes
 // the state, draws the next path / target orientation (unless the set-point is fixed), installs a fresh
 // controller and writes the observation of the fresh state.  Out of line: one environment in max_steps takes it.
+// ep_prev: the environment's episode counter before this reset (the step kernel stages it with the other epilogue inputs)
 template <typename T, int MODE>
-__device__ MVRL_NOINLINE void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long i) {
+__device__ MVRL_NOINLINE void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long i, uint32_t ep_prev) {
     const long ld = a.ld;
     const Rov6Dev<T>& P = a.P;
     if (a.term_obs != nullptr) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) a.term_obs[k * ld + i] = a.obs[k * ld + i];
     }
-    const uint32_t ep = a.episode[i] + 1u;
+    const uint32_t ep = ep_prev + 1u;
     a.episode[i] = ep;
     a.istep[i] = 0;
 #pragma unroll
@@ -256,6 +257,12 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     // DRAM latency hides behind the RK4 loop without holding 6 (12) registers across it - as registers they were
     // spilled (r1i profile: STL in the prologue and LDL / long-scoreboard stalls in the epilogue).
     __shared__ V s_path[6][StepLaunch<V>::BLOCK];
+    __shared__ uint32_t s_episode[StepLaunch<V>::BLOCK][L];   // read by the auto-reset only: one environment in max_steps
+    if (a.auto_reset) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_episode[threadIdx.x][0]);
+        if (L == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.episode + i0));
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(a.episode + i0));
+    }
     {
         const char* p = reinterpret_cast<const char*>(a.path + i0);
 #pragma unroll
@@ -516,7 +523,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-        if (reset_lane[l]) rov6_auto_reset_env<T, MODE>(a, i0 + l);
+        if (reset_lane[l]) rov6_auto_reset_env<T, MODE>(a, i0 + l, s_episode[threadIdx.x][l]);
     }
 }
 

@@ -280,7 +280,7 @@ rov6_step_ws_kernel(const __grid_constant__ Rov6StepArgs<float> a) {
                     if (a.stats != nullptr) stats_accumulate_counts(a.stats, n_done, len, n_bad);
 #pragma unroll
                     for (int l = 0; l < 2; ++l) {
-                        if (flags & (WS_RESET0 << l)) rov6_auto_reset_env<float, ACT_RPM>(a, i0 + l);
+                        if (flags & (WS_RESET0 << l)) rov6_auto_reset_env<float, ACT_RPM>(a, i0 + l, a.episode[i0 + l]);
                     }
                 }
                 const long t_new = cta_first + c + k * tile_stride;
