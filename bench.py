@@ -362,7 +362,7 @@ def run_ours(args, rank, local_rank, world):
                     "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                             "bytes_per_env_step": nbytes, "peak_source": peak_src}}
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             rate, secs, used = cpu_port_rate(32768, args.cpu_steps)
             cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": "%d envs x %d env steps of the same workload, C port of the reference loop, %d threads, %.1f s" %
