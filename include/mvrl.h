@@ -108,7 +108,10 @@ typedef struct MvrlRov6Config {
 } MvrlRov6Config;
 
 /* Device buffers of one batch of 6DoF environments.  T = element type.
- * Nullable members may be NULL. */
+ * Nullable members may be NULL.  Every row must be allocated to its full leading dimension ld (ld >= n):
+ * the fp32 kernels that carry two environments per thread access rows in 8-byte units, so the padding element
+ * after an odd n is read (never written).  That path needs ld even and 8-byte aligned rows (2-byte for done);
+ * other layouts silently take the one-environment-per-thread kernels. */
 typedef struct MvrlRov6Buffers {
     void* state;        /* T [12][ld] x y z phi theta psi u v w p q r       in/out */
     void* action;       /* T [8|6][ld] per action_mode                       in     */
