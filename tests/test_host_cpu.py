@@ -122,3 +122,23 @@ def test_episode_stats_allreduce_gloo_world2(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "rank %d ok" % r in out
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs first): exactly one JSON line on stdout with the
+    contract's keys, whatever libraries write to stdout / stderr meanwhile."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
