@@ -1,0 +1,32 @@
+"""GPU: bench.py keeps its contract (one JSON line; metric / roofline / cpu_baseline / e2e / clocks / gpu_launches)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bench_line_contract_on_a_small_batch():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--envs", "8192", "--cpu-steps", "5"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["metric"] == "BlueROV2 6DoF env-steps/sec" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["value"] > 0 and d["gpu_launches"] == 20
+    r = d["roofline"]
+    assert r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["hbm"]["unit"] == "GB/s"
+    assert r["executed_frac"] < r["frac"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8192 * 8 * 4 and e["d2h_bytes_per_step"] == 8192 * (9 * 4 + 4 + 1)
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
