@@ -131,7 +131,7 @@ _lib = None
 
 def build(verbose=False):
     """Compile libmvrl.so in-tree with nvcc for sm_100a (csrc/Makefile)."""
-    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    res = subprocess.run(["make", "-j8", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)

@@ -128,8 +128,9 @@ struct MvrlRov6 {
     MvrlRov6Params p;
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
-    bool ws;  // warp-specialised persistent step kernel for fp32 / rpm / default sparsity (MVRL_WS=1 in the environment enables it)
     bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
+    bool small_shape;  // small batches use the 64-thread / 128-register launch shape (MVRL_NO_SMALL_SHAPE=1 disables it)
+    int sm_count;
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
     // resources of mvrl_rov6_step_host (created on first use, released by destroy)
@@ -207,8 +208,6 @@ static bool default_sparsity(const MvrlRov6Params& p) {
     return true;
 }
 
-int mvrl_rov6_ws_prepare(int device);
-
 extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, const MvrlRov6Config* cfg) {
     if (!out || !params || !cfg) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_create: null argument");
     if (cfg->dtype != MVRL_F32 && cfg->dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "dtype must be MVRL_F32 or MVRL_F64");
@@ -223,10 +222,11 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->c = *cfg;
     h->sp = default_sparsity(*params);
     { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
-    { const char* e = getenv("MVRL_WS"); h->ws = (e && e[0] == '1'); }
+    { const char* e = getenv("MVRL_NO_SMALL_SHAPE"); h->small_shape = !(e && e[0] == '1'); }
+    h->sm_count = 148;
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) h->sm_count = v; else cudaGetLastError(); }
     to_dev(*params, h->pf);
     to_dev(*params, h->pd);
-    if (cudaSetDevice(cfg->device) == cudaSuccess) mvrl_rov6_ws_prepare(cfg->device);
     *out = h;
     return MVRL_OK;
 }
@@ -234,7 +234,7 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
 extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) {
     if (!h) return MVRL_OK;
     if (h->hs[0] || h->stage_act || h->stage_obs) {
-        cudaSetDevice(h->c.device);
+        MvrlDeviceGuard guard(h->c.device);
         for (int i = 0; i < MvrlRov6::kStreams; ++i) {
             if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
             if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
@@ -286,40 +286,36 @@ template <typename T> static bool x2_layout_ok(const Rov6StepArgs<T>& a) {
     return true;
 }
 
-// Warp-specialised persistent variant, compiled in its own translation unit (mvrl_rov6_ws.cu)
-int mvrl_rov6_ws_prepare(int device);                                                   // shared-memory opt-in; SM count
-void mvrl_rov6_ws_launch(const Rov6StepArgs<float>& a, int device, cudaStream_t s);
-
 template <typename T, int MODE, bool SP, bool FAST>
-static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
-    const bool x2 = (flags & 1) != 0, ws = (flags & 2) != 0;   // two environments per thread; warp-specialised variant
+static void launch_step(const Rov6StepArgs<T>& a, int flags, int sm_count, cudaStream_t s) {
+    const bool x2 = (flags & 1) != 0;   // two environments per thread
     // the four RK4 stages are unrolled: measured faster than the rolled loop (r1 profile notes)
     constexpr int UNROLL = MVRL_STAGE_UNROLL(T);
     if constexpr (sizeof(T) == 4) {
-        if constexpr (MODE == ACT_RPM && SP && !FAST) {
-            if (ws && x2 && x2_layout_ok(a) && a.aux == nullptr) {
-                int device = 0;
-                cudaGetDevice(&device);
-                mvrl_rov6_ws_launch(a, device, s);
-                return;
-            }
-        }
         if (x2 && x2_layout_ok(a)) {
-            rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for((a.n + 1) / 2, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
+            const int64_t threads = (a.n + 1) / 2;
+            if constexpr (SP && !FAST) {
+                // small shard: every warp fits on the machine at once at 16 warps per SM (see StepLaunch<F2, 1>)
+                if ((flags & 4) == 0 && (threads + 31) / 32 <= 16 * (int64_t)sm_count) {
+                    rov6_step_kernel<F2, MODE, SP, FAST, UNROLL, 1><<<grid_for(threads, StepLaunch<F2, 1>::BLOCK), StepLaunch<F2, 1>::BLOCK, 0, s>>>(a);
+                    return;
+                }
+            }
+            rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
             return;
         }
     }
     rov6_step_kernel<T, MODE, SP, FAST, UNROLL><<<grid_for(a.n, MVRL_STEP_BLOCK), MVRL_STEP_BLOCK, 0, s>>>(a);
 }
 template <typename T, bool FAST>
-static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, int x2, cudaStream_t s) {
+static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, int x2, int sm_count, cudaStream_t s) {
     switch (mode * 2 + (sp ? 1 : 0)) {
-        case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, s); break;
-        case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, s); break;
-        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, x2, s); break;
-        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, x2, s); break;
-        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, x2, s); break;
-        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, x2, s); break;
+        case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, sm_count, s); break;
+        case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, sm_count, s); break;
+        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, x2, sm_count, s); break;
+        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, x2, sm_count, s); break;
+        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, x2, sm_count, s); break;
+        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, x2, sm_count, s); break;
     }
 }
 
@@ -333,7 +329,10 @@ static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t first
     a.dt = T(h->c.dt); a.h = T(h->c.dt / h->c.n_sub);
     a.hh = T(0.5) * a.h; a.h6 = a.h / T(6); a.h3 = a.h / T(3);   // in T arithmetic, like the kernel used to
     const T dtc[2] = {T(0), a.hh};
-    for (int i = 0; i < 2; ++i) { a.pid_inv_dt[i] = T(1) / (dtc[i] > T(1e-9) ? dtc[i] : T(1e-9)); a.pid_half_dt[i] = T(0.5) * dtc[i]; }
+    for (int i = 0; i < 2; ++i) {
+        a.pid_inv_dt[i] = T(1) / (dtc[i] > T(1e-9) ? dtc[i] : T(1e-9)); a.pid_half_dt[i] = T(0.5) * dtc[i];
+        for (int k = 0; k < 6; ++k) a.pid_kd_inv_dt[i][k] = P.pKd[k] * a.pid_inv_dt[i];
+    }
     a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0 + (unsigned long long)first;
     a.auto_reset = h->c.auto_reset; a.fixed_sp = h->c.fixed_sp;
@@ -353,19 +352,19 @@ static int check_step_args(const MvrlRov6* h, int64_t first, int64_t n, int64_t 
 static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, cudaStream_t s) {
     if (h->c.dtype == MVRL_F64) {
         Rov6StepArgs<double> a; fill_step_args(h, h->pd, first, n, ld, b, a);
-        dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, s);
+        dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, h->sm_count, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
-        const int flags = (h->x2 ? 1 : 0) | (h->ws ? 2 : 0);
-        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, s);
-        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, s);
+        const int flags = (h->x2 ? 1 : 0) | (h->small_shape ? 0 : 4);
+        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
+        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
     }
 }
 
 extern "C" MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
     { const int rc = check_step_args(h, 0, n, ld, b, "mvrl_rov6_step"); if (rc != MVRL_OK) return rc; }
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     launch_step_range(h, 0, n, ld, b, (cudaStream_t)stream);
     return check_launch("rov6_step");
 }
@@ -373,7 +372,7 @@ extern "C" MVRL_API int mvrl_rov6_step(MvrlRov6* h, int64_t n, int64_t ld, const
 extern "C" MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, mvrl_stream_t stream) {
     { const int rc = check_step_args(h, first, n, ld, b, "mvrl_rov6_step_range"); if (rc != MVRL_OK) return rc; }
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     launch_step_range(h, first, n, ld, b, (cudaStream_t)stream);
     return check_launch("rov6_step_range");
 }
@@ -542,7 +541,7 @@ extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, 
     { const int rc = check_step_args(h, 0, n, ld, b, "mvrl_rov6_step_host"); if (rc != MVRL_OK) return rc; }
     if (n == 0) return MVRL_OK;   // an empty batch has no host arrays to name
     if (!actions_host || !obs_host) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_step_host: actions_host and obs_host are required");
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     const size_t es = h->c.dtype == MVRL_F64 ? 8 : 4;
     const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;
     const size_t need_act = (size_t)n * n_act * es, need_obs = (size_t)n * 9 * es;
@@ -627,7 +626,7 @@ extern "C" MVRL_API int mvrl_rov6_derivs(MvrlRov6* h, int64_t n, int64_t ld, con
         return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_derivs: act is required");
     }
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->c.dtype == MVRL_F64) return derivs_impl<double>(h, h->pd, n, ld, state, act, t, setpoint, ctrl, dstate, aux, s);
     return derivs_impl<float>(h, h->pf, n, ld, state, act, t, setpoint, ctrl, dstate, aux, s);
@@ -657,7 +656,7 @@ extern "C" MVRL_API int mvrl_rov6_reset(MvrlRov6* h, int64_t n, int64_t ld, cons
     if (!b->state || !b->obs || !b->istep || !b->setpoint || !b->path)
         return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_reset: state/obs/istep/setpoint/path are required");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->c.dtype == MVRL_F64) return reset_impl<double>(h, h->pd, n, ld, b, mask, initial_setpoint_host, s);
     return reset_impl<float>(h, h->pf, n, ld, b, mask, initial_setpoint_host, s);
@@ -676,7 +675,7 @@ extern "C" MVRL_API int mvrl_rov6_pid(MvrlRov6* h, int64_t n, int64_t ld, const 
     if (!h || !pose || !t || !setpoint || !ctrl || !forces) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_pid: null argument");
     if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_pid: need 0 <= n <= ld");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return pid_impl<double>(h->pd, n, ld, pose, t, setpoint, ctrl, forces, (cudaStream_t)stream);
     return pid_impl<float>(h->pf, n, ld, pose, t, setpoint, ctrl, forces, (cudaStream_t)stream);
 }
@@ -714,6 +713,7 @@ extern "C" MVRL_API int mvrl_coordinate_transform(int dtype, int dof, int64_t n,
     if ((dof != 3 && dof != 6) || !psi || !out || (dof == 6 && (!phi || !theta))) return mvrl_fail(MVRL_EINVAL, "mvrl_coordinate_transform: bad argument");
     if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_coordinate_transform: need 0 <= n <= ld");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, psi, "mvrl_coordinate_transform");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) coordinate_transform_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(dof, n, ld, (const double*)phi, (const double*)theta, (const double*)psi, (double*)out);
     else if (dtype == MVRL_F32) coordinate_transform_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(dof, n, ld, (const float*)phi, (const float*)theta, (const float*)psi, (float*)out);
@@ -730,6 +730,7 @@ __global__ void angle_error_kernel(long n, const T* a, const T* b, T* out) {
 extern "C" MVRL_API int mvrl_angle_error(int dtype, int64_t n, const void* psi_d, const void* psi, void* out, mvrl_stream_t stream) {
     if (!psi_d || !psi || !out || n < 0) return mvrl_fail(MVRL_EINVAL, "mvrl_angle_error: bad argument");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, psi, "mvrl_angle_error");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) angle_error_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, (const double*)psi_d, (const double*)psi, (double*)out);
     else if (dtype == MVRL_F32) angle_error_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, (const float*)psi_d, (const float*)psi, (float*)out);
@@ -753,6 +754,7 @@ __global__ void body_axes_kernel(long n, long ld, const T* ang, T* out) {
 extern "C" MVRL_API int mvrl_body_axes(int dtype, int64_t n, int64_t ld, const void* angles, void* out, mvrl_stream_t stream) {
     if (!angles || !out || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_body_axes: bad argument");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, angles, "mvrl_body_axes");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) body_axes_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)angles, (double*)out);
     else if (dtype == MVRL_F32) body_axes_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)angles, (float*)out);
@@ -785,7 +787,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 
 extern "C" MVRL_API int mvrl_measure_fma_peak(int dtype, int device, int iters, double* tflops_out, double* ms_out) {
     if (!tflops_out || iters < 1) return mvrl_fail(MVRL_EINVAL, "mvrl_measure_fma_peak: bad argument");
-    MVRL_CUDA(cudaSetDevice(device));
+    MVRL_ON_DEVICE(device);
     cudaDeviceProp prop;
     MVRL_CUDA(cudaGetDeviceProperties(&prop, device));
     constexpr int CH = 8;
@@ -826,7 +828,7 @@ __global__ void rov6_thruster_kernel(T thrust_k, long n, const T* rpm, T* F) {
 extern "C" MVRL_API int mvrl_rov6_thruster_model(MvrlRov6* h, int64_t n, const void* rpm, void* F, mvrl_stream_t stream) {
     if (!h || !rpm || !F || n < 0) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_thruster_model: bad argument");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->c.dtype == MVRL_F64) rov6_thruster_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(h->pd.thrust_k, n, (const double*)rpm, (double*)F);
     else rov6_thruster_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(h->pf.thrust_k, n, (const float*)rpm, (float*)F);
@@ -857,6 +859,7 @@ extern "C" MVRL_API int mvrl_frame_rotate(int dtype, int64_t n, int64_t ld, cons
                                           mvrl_stream_t stream) {
     if (!axes || !v || !out || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_frame_rotate: bad argument");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, v, "mvrl_frame_rotate");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) frame_rotate_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)axes, (const double*)v, (double*)out, to_vehicle);
     else if (dtype == MVRL_F32) frame_rotate_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)axes, (const float*)v, (float*)out, to_vehicle);

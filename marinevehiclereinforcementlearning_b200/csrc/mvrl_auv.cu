@@ -108,7 +108,7 @@ extern "C" MVRL_API int mvrl_auv_step(MvrlAuv* h, int64_t n, int64_t ld, const M
     if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_step: episode is required with auto_reset");
     if (h->p.variant == MVRL_AUV_CYL && !b->iwp) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_step: iwp is required for the AuvEnvCyl variant");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return auv_step_impl<double>(h, n, ld, b, (cudaStream_t)stream);
     return auv_step_impl<float>(h, n, ld, b, (cudaStream_t)stream);
 }
@@ -132,7 +132,7 @@ extern "C" MVRL_API int mvrl_auv_reset(MvrlAuv* h, int64_t n, int64_t ld, const 
         return mvrl_fail(MVRL_EINVAL, "mvrl_auv_reset: missing required buffer");
     if (h->p.variant == MVRL_AUV_CYL && !b->iwp) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_reset: iwp is required for the AuvEnvCyl variant");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return auv_reset_impl<double>(h, n, ld, b, mask, init, (cudaStream_t)stream);
     return auv_reset_impl<float>(h, n, ld, b, mask, init, (cudaStream_t)stream);
 }
@@ -142,6 +142,7 @@ extern "C" MVRL_API int mvrl_flow_interp(int dtype, const void* field, int nt, i
     if (!field || !t || !xy || !out || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_flow_interp: bad argument");
     if (nt < 2 || ny < 2 || nx < 2 || (nc != 2 && nc != 3)) return mvrl_fail(MVRL_EINVAL, "mvrl_flow_interp: need nt, ny, nx >= 2 and nc in {2, 3}");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, field, "mvrl_flow_interp");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) flow_interp_kernel<double><<<mvrl_grid_for(n, 128), 128, 0, s>>>(flow_dev<double>(field, nt, ny, nx, nc, dx, dy, dt), n, ld, (const double*)t, (const double*)xy, (double*)out);
     else if (dtype == MVRL_F32) flow_interp_kernel<float><<<mvrl_grid_for(n, 128), 128, 0, s>>>(flow_dev<float>(field, nt, ny, nx, nc, dx, dy, dt), n, ld, (const float*)t, (const float*)xy, (float*)out);
@@ -153,6 +154,7 @@ extern "C" MVRL_API int mvrl_flow_scale(int dtype, int64_t cells, const void* ba
                                         double turbScale, mvrl_stream_t stream) {
     if (!base || !out || cells < 0 || (nc_out != 2 && nc_out != 3)) return mvrl_fail(MVRL_EINVAL, "mvrl_flow_scale: bad argument");
     if (cells == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(out, base, "mvrl_flow_scale");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) flow_scale_kernel<double><<<mvrl_grid_for(cells, 256), 256, 0, s>>>(cells, (const double*)base, (double*)out, nc_out, velocityScale, turbScale);
     else if (dtype == MVRL_F32) flow_scale_kernel<float><<<mvrl_grid_for(cells, 256), 256, 0, s>>>(cells, (const float*)base, (float*)out, nc_out, (float)velocityScale, (float)turbScale);
@@ -169,6 +171,7 @@ extern "C" MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t 
     if (n < 0 || ld < n || buffer_size < 1 || pos < 0 || pos >= buffer_size || n_transforms < 1 || n_transforms > 5 || n_transforms > buffer_size)
         return mvrl_fail(MVRL_EINVAL, "mvrl_replay_add_symmetric: bad size argument");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(buf_obs, obs, "mvrl_replay_add_symmetric");
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned g = mvrl_grid_for(n * n_transforms, 256);
     if (dtype == MVRL_F64)

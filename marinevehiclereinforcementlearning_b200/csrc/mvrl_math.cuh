@@ -90,6 +90,17 @@ template <typename T> __device__ __forceinline__ bool visnan(T a) { return a != 
 __device__ __forceinline__ B2 visnan(F2 a) { return B2{a.v.x != a.v.x, a.v.y != a.v.y}; }
 template <typename T> __device__ __forceinline__ T vsel(bool m, T a, T b) { return m ? a : b; }
 __device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) { return F2(m.x ? a.v.x : b.v.x, m.y ? a.v.y : b.v.y); }
+// 1.0 / 0.0 masks for multiplicative selects: ONE instruction per lane (FSET.BF) where compare + select takes two, and the
+// multiply that applies them is a packed FMA-pipe instruction - the set-point kernel was bound by the ALU pipe (profiles/
+// r1_x: pipe_alu 40 % of issue slots against pipe_fma 32 %), so selects of the form "x or 0" are written mask * x.
+template <typename T> __device__ __forceinline__ T vmask_lt(T a, T b) { return a < b ? T(1) : T(0); }
+template <typename T> __device__ __forceinline__ T vmask_ge(T a, T b) { return a >= b ? T(1) : T(0); }
+template <typename T> __device__ __forceinline__ T vmask_le(T a, T b) { return a <= b ? T(1) : T(0); }
+__device__ __forceinline__ F2 vmask_lt(F2 a, F2 b) { return F2(a.v.x < b.v.x ? 1.0f : 0.0f, a.v.y < b.v.y ? 1.0f : 0.0f); }
+__device__ __forceinline__ F2 vmask_ge(F2 a, F2 b) { return F2(a.v.x >= b.v.x ? 1.0f : 0.0f, a.v.y >= b.v.y ? 1.0f : 0.0f); }
+__device__ __forceinline__ F2 vmask_le(F2 a, F2 b) { return F2(a.v.x <= b.v.x ? 1.0f : 0.0f, a.v.y <= b.v.y ? 1.0f : 0.0f); }
+template <typename T> __device__ __forceinline__ bool vge(T a, T b) { return a >= b; }
+__device__ __forceinline__ B2 vge(F2 a, F2 b) { return B2{a.v.x >= b.v.x, a.v.y >= b.v.y}; }
 __device__ __forceinline__ bool vany(bool m) { return m; }
 __device__ __forceinline__ bool vany(B2 m) { return m.x || m.y; }
 __device__ __forceinline__ float vcopysign(float mag, float sign) { return copysignf(mag, sign); }
@@ -141,11 +152,32 @@ template <typename T> __device__ __forceinline__ T angle_error(T psi_d, T psi) {
 #ifndef MVRL_POSE_COMP
 #define MVRL_POSE_COMP 1
 #endif
+#ifndef MVRL_PID_DPOSE
+#define MVRL_PID_DPOSE 1   // fp32 step kernels: PID error differences from pose increments (rov6_model.cuh, pid6_core_dp)
+#endif
 #ifndef MVRL_TRIG_ANCHOR
 #define MVRL_TRIG_ANCHOR 1
 #endif
 __device__ __forceinline__ F2 angle_error(F2 psi_d, F2 psi) {
     return F2(angle_error(psi_d.v.x, psi.v.x), angle_error(psi_d.v.y, psi.v.y));
+}
+// The same function, straight-line for any value type.  For |d| < 2 pi the selection of resources.py:92-95 (a = d % 2pi,
+// b = -d % 2pi, a if a < b else -b) is d shifted by one turn when it lies outside [-pi, pi): a < b <=> d < -pi for
+// negative d (result d + 2pi) and a >= b <=> d >= pi for positive d (result d - 2pi); both sums are exact where they
+// apply (Sterbenz), so the value is the reference's bit for bit - except that equal angles give +0 where the reference
+// gives -0.0.  Anything beyond one turn takes the exact out-of-line path.
+#define MVRL_PI 3.141592653589793238462643383279
+template <typename T> __device__ MVRL_NOINLINE T angle_error_general(T psi_d, T psi) { return angle_error(psi_d, psi); }
+__device__ __forceinline__ F2 angle_error_general(F2 psi_d, F2 psi) {
+    return F2(angle_error_general(psi_d.v.x, psi.v.x), angle_error_general(psi_d.v.y, psi.v.y));
+}
+template <typename V> __device__ __forceinline__ V angle_error_v(V psi_d, V psi) {
+    using S = typename VT<V>::S;
+    const V d = psi_d - psi;
+    const V turns = vmask_lt(d, V(S(-MVRL_PI))) - vmask_ge(d, V(S(MVRL_PI)));
+    V e = fmaf_t(V(S(MVRL_TWO_PI)), turns, d);
+    if (vany(vge(tabs(d), V(S(MVRL_TWO_PI))))) e = angle_error_general(psi_d, psi);
+    return e;
 }
 
 // y += inc with a Kahan carry (compensated summation across RK4 sub-steps)

@@ -108,7 +108,7 @@ extern "C" MVRL_API int mvrl_rov3_step(MvrlRov3* h, int64_t n, int64_t ld, const
     if (h->c.action_mode == MVRL_ACT_SETPOINT && !b->ctrl) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_step: ctrl is required in set-point mode");
     if (h->c.auto_reset && !b->episode) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_step: episode is required with auto_reset");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return step3_impl<double>(h, h->pd, n, ld, b, (cudaStream_t)stream);
     return step3_impl<float>(h, h->pf, n, ld, b, (cudaStream_t)stream);
 }
@@ -130,7 +130,7 @@ extern "C" MVRL_API int mvrl_rov3_derivs(MvrlRov3* h, int64_t n, int64_t ld, con
     if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_derivs: need 0 <= n <= ld");
     if (h->c.action_mode == MVRL_ACT_SETPOINT ? (!t || !setpoint || !ctrl) : !act) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_derivs: missing inputs for the action mode");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return derivs3_impl<double>(h, h->pd, n, ld, state, act, t, setpoint, ctrl, dstate, aux, (cudaStream_t)stream);
     return derivs3_impl<float>(h, h->pf, n, ld, state, act, t, setpoint, ctrl, dstate, aux, (cudaStream_t)stream);
 }
@@ -153,7 +153,7 @@ extern "C" MVRL_API int mvrl_rov3_reset(MvrlRov3* h, int64_t n, int64_t ld, cons
     if (n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_reset: need 0 <= n <= ld");
     if (!b->state || !b->obs || !b->istep || !b->setpoint || !b->path) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_reset: state/obs/istep/setpoint/path are required");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     if (h->c.dtype == MVRL_F64) return reset3_impl<double>(h, h->pd, n, ld, b, mask, initial_setpoint_host, (cudaStream_t)stream);
     return reset3_impl<float>(h, h->pf, n, ld, b, mask, initial_setpoint_host, (cudaStream_t)stream);
 }
@@ -161,7 +161,7 @@ extern "C" MVRL_API int mvrl_rov3_reset(MvrlRov3* h, int64_t n, int64_t ld, cons
 extern "C" MVRL_API int mvrl_rov3_thruster_model(MvrlRov3* h, int64_t n, const void* u, const void* rpm, void* F, void* X, mvrl_stream_t stream) {
     if (!h || !u || !rpm || !F || !X || n < 0) return mvrl_fail(MVRL_EINVAL, "mvrl_rov3_thruster_model: bad argument");
     if (n == 0) return MVRL_OK;
-    MVRL_CUDA(cudaSetDevice(h->c.device));
+    MVRL_ON_DEVICE(h->c.device);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->c.dtype == MVRL_F64) rov3_thruster_kernel<double><<<mvrl_grid_for(n, 128), 128, 0, s>>>(h->pd, n, (const double*)u, (const double*)rpm, (double*)F, (double*)X);
     else rov3_thruster_kernel<float><<<mvrl_grid_for(n, 128), 128, 0, s>>>(h->pf, n, (const float*)u, (const float*)rpm, (float*)F, (float*)X);
@@ -172,6 +172,7 @@ extern "C" MVRL_API int mvrl_rov3_thruster_model(MvrlRov3* h, int64_t n, const v
 extern "C" MVRL_API int mvrl_los_navigation(int dtype, int64_t n, int64_t ld, const void* obs, void* action, double rnav, mvrl_stream_t stream) {
     if (!obs || !action || n < 0 || ld < n) return mvrl_fail(MVRL_EINVAL, "mvrl_los_navigation: bad argument");
     if (n == 0) return MVRL_OK;
+    MVRL_ON_DEVICE_OF(action, obs, "mvrl_los_navigation");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) los_navigation_kernel<double><<<mvrl_grid_for(n, 128), 128, 0, s>>>(n, ld, (const double*)obs, (double*)action, rnav);
     else if (dtype == MVRL_F32) los_navigation_kernel<float><<<mvrl_grid_for(n, 128), 128, 0, s>>>(n, ld, (const float*)obs, (float*)action, (float)rnav);

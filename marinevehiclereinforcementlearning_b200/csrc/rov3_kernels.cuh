@@ -56,6 +56,28 @@ __device__ __forceinline__ void pid3(const Rov3Dev<T>& P, T (&e_old)[3], T (&e_i
     }
 }
 
+// The fp32 step kernel's variant: e - eOld from the pose increment between two consecutive calls (see pid6_core_dp in
+// rov6_model.cuh for the why); dpose[k] = pose_k - pose_k of the previous call, primed with eOld - e for the first call
+// of an env step.  A 2 pi jump of the wrapped yaw error falls back to the literal difference.
+template <typename T>
+__device__ __forceinline__ void pid3_dp(const Rov3Dev<T>& P, T (&e_old)[3], T (&e_int)[3], const T (&sp)[3], T x, T y, T psi,
+                                        const T (&dpose)[3], T dtc, T (&out)[3]) {
+    T e[3] = {sp[0] - x, sp[1] - y, angle_error(sp[2], psi)};
+    const T inv_dt = T(1) / tmax(T(1e-9), dtc);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T de = -dpose[k];
+        if (k == 2) { const T dd = e[2] - e_old[2]; if (tabs(dd) > T(1)) de = dd; }
+        const T dedt = de * inv_dt;
+        T ei = e_int[k] + T(0.5) * (e_old[k] + e[k]) * dtc;
+        if (tabs(e[k]) > P.pWind[k]) ei = T(0);
+        const T c = P.pKp[k] * e[k] + P.pKd[k] * dedt + P.pKi[k] * ei;
+        out[k] = tmax(-P.pMax[k], tmin(P.pMax[k], c));
+        e_int[k] = ei;
+        e_old[k] = e[k];
+    }
+}
+
 // 3DoF.py:159-168: earth-frame PID output -> body frame -> rpm
 template <typename T>
 __device__ __forceinline__ void allocate3(const Rov3Dev<T>& P, T s, T c, const T (&cvl)[3], T (&gcf)[3], T (&rpm)[4]) {
@@ -165,18 +187,30 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) rpm[k] = act[k];
     }
+    // RK4 as in rov6_step_kernel: fp32 pose advanced by the summed increment with a Kahan carry
+    constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
+    constexpr bool DPOSE = (MODE == ACT_SETPOINT) && COMP && (MVRL_PID_DPOSE != 0);
+    T dpose[3] = {T(0), T(0), T(0)}, off[3] = {T(0), T(0), T(0)};
+    if constexpr (DPOSE) {   // first call of the env step: literal e - eOld (a fresh controller has eOld = e)
+        const T e0[3] = {sp[0] - y[0], sp[1] - y[1], angle_error(sp[2], y[2])};
+        if (e_old[0] != e_old[0]) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e_old[k] = e0[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dpose[k] = e_old[k] - e0[k];
+    }
     auto f = [&](const T (&s)[6], T (&k)[6], T dtc) {
         T sn, cs;
         sincos_t<T, FAST>(s[2], &sn, &cs);
         if constexpr (MODE == ACT_SETPOINT) {
             T cvl[3];
-            pid3(P, e_old, e_int, sp, s[0], s[1], s[2], dtc, cvl);
+            if constexpr (DPOSE) pid3_dp(P, e_old, e_int, sp, s[0], s[1], s[2], dpose, dtc, cvl);
+            else pid3(P, e_old, e_int, sp, s[0], s[1], s[2], dtc, cvl);
             allocate3(P, sn, cs, cvl, gcf, rpm);
         }
         derivs3_core(P, sn, cs, s[3], s[4], s[5], rpm, k);
     };
-    // RK4 as in rov6_step_kernel: fp32 pose advanced by the summed increment with a Kahan carry
-    constexpr bool COMP = (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0);
     const T h = a.h, hh = a.hh, h6 = a.h6, h3 = a.h3;
     T carry[3] = {T(0), T(0), T(0)};
     for (int sub = 0; sub < a.n_sub; ++sub) {
@@ -191,7 +225,14 @@ rov3_step_kernel(const __grid_constant__ Rov3StepArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 acc[j] = fmaf_t(wk, k[j], acc[j]);
-                if (st < 3) yt[j] = fmaf_t(ck, k[j], y[j]);
+                if (DPOSE && j < 3) {
+                    const T o = (st < 3) ? ck * k[j] : acc[j];   // offset of the next call's pose from y
+                    dpose[j] = o - off[j];
+                    off[j] = (st < 3) ? o : T(0);
+                    if (st < 3) yt[j] = y[j] + o;
+                } else if (st < 3) {
+                    yt[j] = fmaf_t(ck, k[j], y[j]);
+                }
             }
         }
 #pragma unroll

@@ -15,6 +15,7 @@ template <typename T> struct Rov6StepArgs {
     T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
     T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
     T pid_inv_dt[2], pid_half_dt[2];   // 1 / max(1e-9, dtc) and dtc / 2 of the PID for dtc = 0 and dtc = h/2 (host-computed, see h6)
+    T pid_kd_inv_dt[2][6];             // Kd[k] * pid_inv_dt[half]: derivative gain per unit of e - eOld (fp32 set-point kernels)
     T dt, h, hh, h6, h3;   // env step, RK4 step h = dt / n_sub and h/2, h/6, h/3 - computed on the host: kernel arguments reach the
                            // FMAs through uniform registers, whereas a value computed in the kernel occupies a vector register and
                            // makes every y + c k update an FMA with three register sources (3 instead of 2 pipe cycles as FFMA2)
@@ -202,8 +203,13 @@ __device__ MVRL_NOINLINE void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long
 #ifndef MVRL_STEP_MINB_X2
 #define MVRL_STEP_MINB_X2 3   // <= 168 registers: 3 CTAs = 12 warps per SM (measured best, profiles/ r1e notes)
 #endif
-template <typename V> struct StepLaunch { static constexpr int BLOCK = MVRL_STEP_BLOCK, MINB = (sizeof(V) == 4 ? MVRL_STEP_MINB : 1); };
-template <> struct StepLaunch<F2> { static constexpr int BLOCK = MVRL_STEP_BLOCK_X2, MINB = MVRL_STEP_MINB_X2; };
+// SHAPE 0: the throughput shape.  SHAPE 1 (F2 only): the small-shard shape - 64-thread CTAs at <= 128 registers, 16 warps per
+// SM.  A 131 072-environment shard (1 Mi environments over 8 GPUs) is 2048 warps: at 168 registers only 12 x 148 = 1776 of
+// them are resident and the rest runs as a second, nearly empty wave (31.1 us per step measured where 1/8 of the 1 Mi
+// launch is 23.1 us); at 128 registers all of them are resident at once, and 2-warp CTAs spread them 14 / 13 per SM.
+template <typename V, int SHAPE = 0> struct StepLaunch { static constexpr int BLOCK = MVRL_STEP_BLOCK, MINB = (sizeof(V) == 4 ? MVRL_STEP_MINB : 1); };
+template <> struct StepLaunch<F2, 0> { static constexpr int BLOCK = MVRL_STEP_BLOCK_X2, MINB = MVRL_STEP_MINB_X2; };
+template <> struct StepLaunch<F2, 1> { static constexpr int BLOCK = 64, MINB = 8; };
 
 // SoA element access for one thread: environments i0 .. i0 + L - 1 of row p
 template <typename V, typename S> __device__ __forceinline__ V load_v(const S* p, long i0, bool pair) {
@@ -222,8 +228,8 @@ template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, 
     else { if (pair) *reinterpret_cast<float2*>(p + i0) = x.v; else p[i0] = x.v.x; }
 }
 
-template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
-__global__ void __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
+template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL, int SHAPE = 0>
+__global__ void __launch_bounds__((StepLaunch<V, SHAPE>::BLOCK), (StepLaunch<V, SHAPE>::MINB))
 rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     using T = typename VT<V>::S;
     constexpr int L = VT<V>::L;
@@ -256,8 +262,8 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     // Needed by the epilogue only: the way-points are copied global -> shared with cp.async (LDGSTS) now, so their
     // DRAM latency hides behind the RK4 loop without holding 6 (12) registers across it - as registers they were
     // spilled (r1i profile: STL in the prologue and LDL / long-scoreboard stalls in the epilogue).
-    __shared__ V s_path[6][StepLaunch<V>::BLOCK];
-    __shared__ uint32_t s_episode[StepLaunch<V>::BLOCK][L];   // read by the auto-reset only: one environment in max_steps
+    __shared__ V s_path[6][StepLaunch<V, SHAPE>::BLOCK];
+    __shared__ uint32_t s_episode[StepLaunch<V, SHAPE>::BLOCK][L];   // read by the auto-reset only: one environment in max_steps
     if (a.auto_reset) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_episode[threadIdx.x][0]);
         if (L == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.episode + i0));
@@ -298,9 +304,18 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         for (int k = 3; k < 6; ++k) sp[k] = load_v<V>(a.setpoint + k * ld, i0, pair);
     }
 
+    // fp32 set-point mode: the PID's e - eOld comes from the pose increments between consecutive calls (pid6_core_dp)
+    constexpr bool DPOSE = (MODE == ACT_SETPOINT) && (sizeof(T) == 4) && !FAST && (MVRL_POSE_COMP != 0) && (MVRL_PID_DPOSE != 0);
+    V dpose[6], off[6];   // pose of this call - pose of the previous call; offset of this call's pose from y
     if constexpr (MODE == ACT_SETPOINT) {
         const V pose0[6] = {y[0], y[1], y[2], y[3], y[4], y[5]};
         pid6_prime(e_old, sp, pose0);
+        if constexpr (DPOSE) {   // first call of the env step: the set-point has moved, the literal e - eOld is the right one
+            V e0[6];
+            pid6_error(sp, pose0, e0);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { dpose[k] = e_old[k] - e0[k]; off[k] = V(T(0)); }
+        }
     }
 
     V H[6];       // thruster wrench of the current evaluation
@@ -322,7 +337,10 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
         if constexpr (MODE != ACT_RPM) {
             if constexpr (MODE == ACT_SETPOINT) {
                 const V pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
-                pid6_core<false>(P, e_old, e_int, sp, pose, a.pid_inv_dt[half], a.pid_half_dt[half], gcf);
+                if constexpr (DPOSE) {
+                    if (half) pid6_core_dp<true>(P, e_old, e_int, sp, pose, dpose, a.pid_kd_inv_dt[1], a.pid_half_dt[1], gcf);
+                    else pid6_core_dp<false>(P, e_old, e_int, sp, pose, dpose, a.pid_kd_inv_dt[0], a.pid_half_dt[0], gcf);
+                } else pid6_core<false>(P, e_old, e_int, sp, pose, a.pid_inv_dt[half], a.pid_half_dt[half], gcf);
             }
             allocate_demand<V, SP>(P, g, gcf, dem);
             V F[8];
@@ -364,7 +382,9 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                     g = g0;
                 } else {
                     const T cp = (st == 3) ? h : hh;          // this stage's state is y + cp * k(previous stage)
-                    const V d0 = V(cp) * k[3], d1 = V(cp) * k[4], d2 = V(cp) * k[5];
+                    V d0, d1, d2;
+                    if constexpr (DPOSE) { d0 = off[3]; d1 = off[4]; d2 = off[5]; }   // the same products, already formed
+                    else { d0 = V(cp) * k[3]; d1 = V(cp) * k[4]; d2 = V(cp) * k[5]; }
                     const V z0 = d0 * d0, z1 = d1 * d1, z2 = d2 * d2;
                     const V zs = z0 + z1 + z2;
                     sincos_delta(g0.sph, g0.cph, d0, z0, &g.sph, &g.cph);
@@ -388,7 +408,15 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
 #pragma unroll
             for (int j = 0; j < 12; ++j) {
                 acc[j] = fmaf_t(V(wk), k[j], acc[j]);
-                if (st < 3) yt[j] = fmaf_t(V(ck), k[j], y[j]);
+                if (DPOSE && j < 6) {
+                    // next call's pose is y + o (stages 2-4) or y + the RK4 increment (first stage of the next sub-step)
+                    const V o = (st < 3) ? V(ck) * k[j] : acc[j];
+                    dpose[j] = (st == 0) ? o : o - off[j];   // the first stage sits at y itself: its offset is 0
+                    off[j] = o;
+                    if (st < 3) yt[j] = y[j] + o;
+                } else if (st < 3) {
+                    yt[j] = fmaf_t(V(ck), k[j], y[j]);
+                }
             }
         }
 #pragma unroll

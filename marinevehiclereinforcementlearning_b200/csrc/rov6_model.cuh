@@ -121,7 +121,7 @@ __device__ __forceinline__ void sincos_delta(V s0, V c0, V d, V z, V* s, V* c) {
 // 6DoF.py:271-275 + 233-236: saturate, deadband, static thrust.
 template <typename V, typename S> __device__ __forceinline__ V thruster_force(const Rov6Dev<S>& P, V rpm) {
     V r = tmax(V(-P.rpm_max), tmin(V(P.rpm_max), rpm));
-    r = vsel(vlt(tabs(r), V(P.rpm_db)), V(S(0)), r);
+    r = r * vmask_ge(tabs(r), V(P.rpm_db));   // dead band as a 0 / 1 factor (one FSET per lane + a packed multiply)
     return V(P.thrust_k) * r * tabs(r);
 }
 
@@ -208,10 +208,10 @@ __device__ __forceinline__ V demand_to_force(const Rov6Dev<S>& P, V c) {
     if constexpr (EXACT) {
         return thruster_force(P, demand_to_rpm(P, c));
     } else {
-        const V a = tabs(c);
-        V f = tmin(a, V(P.f_max));
-        f = vsel(vlt(a, V(P.f_db)), V(S(0)), f);
-        return vcopysign(f, c);
+        // two min / max and one compare per lane (ALU pipe), one packed multiply; the round-1 form (|c|, min, select,
+        // copysign) took four ALU instructions per lane and was the largest single consumer of that pipe
+        const V sat = tmax(V(-P.f_max), tmin(V(P.f_max), c));
+        return sat * vmask_ge(tabs(c), V(P.f_db));
     }
 }
 
@@ -408,7 +408,7 @@ __device__ __forceinline__ void kinematics6(const Trig6<V>& g, const V (&nu)[6],
 template <typename V> __device__ __forceinline__ void pid6_error(const V (&sp)[6], const V (&pose)[6], V (&e)[6]) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) e[k] = sp[k] - pose[k];
-    e[5] = angle_error(sp[5], pose[5]);
+    e[5] = angle_error_v(sp[5], pose[5]);
 }
 
 // BlueROV2Heavy6DoF_PID_controller.computeControlForces, 6DoF.py:43-73.
@@ -430,6 +430,41 @@ __device__ __forceinline__ void pid6_core(const Rov6Dev<S>& P, V (&e_old)[6], V 
         V ei = fmaf_t(V(half_dt), eo + e[k], e_int[k]);
         ei = vsel(vgt(tabs(e[k]), V(P.pWind[k])), V(S(0)), ei);
         const V cvl = fmaf_t(V(P.pKi[k]), ei, fmaf_t(V(P.pKd[k]), dedt, V(P.pKp[k]) * e[k]));
+        out[k] = tmax(V(-P.pMax[k]), tmin(V(P.pMax[k]), cvl));
+        e_int[k] = ei;
+        e_old[k] = e[k];
+    }
+}
+
+// The same controller for the fp32 step kernels, with e - eOld taken from the pose INCREMENT between two consecutive
+// calls instead of from two rounded errors.  Inside an env step the set-point is constant, so e - eOld = -(pose -
+// pose_old) exactly, and the step kernel knows that increment as a difference of RK4 offsets c k (a few ulp of the
+// INCREMENT), whereas sp - pose carries half an ulp of the POSE.  It matters because RK4 stages 1 and 3 are evaluated
+// at the same t as the call before them: dedt = (e - eOld) / 1e-9 (6DoF.py:64) turns the SIGN of a ~1e-4 difference
+// into a saturated +-pMax demand, and in fp32 the rounded errors get that sign wrong in ~1e-3 of the calls, the
+// increments in ~1e-7 (measured: tests/test_parity_modes_gpu.py).  dpose[k] = pose_k - (pose_k of the previous call);
+// the wrapped yaw error may jump by 2 pi between two calls - then the literal difference is used (it is large and
+// its sign is not in question).  The caller primes dpose with eOld - e for the first call of an env step, where the
+// set-point has moved and the literal difference is the right one.
+template <bool INTEGRATE, typename V, typename S>
+__device__ __forceinline__ void pid6_core_dp(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_int)[6], const V (&sp)[6],
+                                             const V (&pose)[6], const V (&dpose)[6], const S (&kd_inv_dt)[6], S half_dt, V (&out)[6]) {
+    V e[6];
+    pid6_error(sp, pose, e);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        V de = -dpose[k];
+        if (k == 5) {
+            const V dd = e[5] - e_old[5];
+            de = vsel(vgt(tabs(dd), V(S(1))), dd, de);
+        }
+        // anti-wind-up (6DoF.py:67) folded into the integrator update as a 0 / 1 factor.  INTEGRATE = false: a call at
+        // the same t as the one before it (half_dt = 0) adds nothing to the integral - only the wind-up test applies.
+        V ei = e_int[k];
+        if constexpr (INTEGRATE) ei = fmaf_t(V(half_dt), e_old[k] + e[k], ei);
+        ei = ei * vmask_le(tabs(e[k]), V(P.pWind[k]));
+        // Kd dedt = (Kd / max(1e-9, dt)) (e - eOld): the quotient comes from the host (uniform register)
+        const V cvl = fmaf_t(V(P.pKi[k]), ei, fmaf_t(V(kd_inv_dt[k]), de, V(P.pKp[k]) * e[k]));
         out[k] = tmax(V(-P.pMax[k]), tmin(V(P.pMax[k]), cvl));
         e_int[k] = ei;
         e_old[k] = e[k];

@@ -295,7 +295,7 @@ class _RovVecEnv:
             if mask is None:
                 self._episode += 1
             else:
-                self._episode[:self.num_envs] += mask.to(torch.int32)
+                self._episode[:self.num_envs] += torch.as_tensor(mask).to(device=self.device, dtype=torch.int32)
         self._needs_episode_bump = True
         sp = None
         if initialSetpoint is not None:
@@ -303,7 +303,7 @@ class _RovVecEnv:
             sp = (C.c_double * self.SP_DIM)(*vals)
         m = None
         if mask is not None:
-            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
         _lib.check(h.fn("reset")(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.ptr(m), sp,
                                  _lib.current_stream(self.device)))
         return self.state
@@ -389,7 +389,10 @@ class _RovVecEnv:
         """{episodes, mean_length, mean_return, min_return, max_return,
         nonfinite}.  When torch.distributed is initialised the 8 accumulators
         are all-reduced over the process group (NCCL on GPUs) - the only
-        collective of the framework, off the step path."""
+        collective of the framework, off the step path.  Episodes are counted
+        where they END INSIDE THE KERNEL, i.e. with ``auto_reset=True``; an env
+        created with ``auto_reset=False`` keeps integrating past ``done`` like
+        the reference (6DoF.py:589-592) and reports 0 episodes here."""
         if self._stats is None:
             raise RuntimeError("collect_stats=False")
         from .distributed import reduce_episode_stats

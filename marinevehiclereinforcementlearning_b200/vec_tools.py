@@ -169,8 +169,12 @@ class Sb3VecEnv:
     What ``SubprocVecEnv([make_env(i) ...]) + VecMonitor`` provides in tag_00.../main_00_sbl.py:145-146 - one
     process, one kernel launch per step instead of nProc worker processes and pipes."""
 
-    def __init__(self, env, monitor_file=None):
+    def __init__(self, env, monitor_file=None, flag_time_limit=False):
+        """``flag_time_limit``: add ``TimeLimit.truncated`` to the info of an episode that ended by reaching ``maxSteps``
+        while inside the bounds.  Off by default: the reference envs set ``done`` themselves (no ``TimeLimit`` wrapper), so
+        upstream the key never exists and SB3's off-policy learners do not bootstrap through max-step terminations."""
         self.env = env
+        self.flag_time_limit = bool(flag_time_limit)
         self.num_envs = env.num_envs
         self.observation_space = Box(-1.0, 1.0, shape=(env.lenObs,), dtype=np.float32)
         self.action_space = Box(-1.0, 1.0, shape=(env.lenAction,), dtype=np.float32)
@@ -211,7 +215,8 @@ class Sb3VecEnv:
             for j, i in enumerate(idx):
                 ep = {"r": round(float(self._ret[i]), 6), "l": int(self._len[i]), "t": now}
                 infos[i]["episode"] = ep
-                infos[i]["TimeLimit.truncated"] = bool(self._len[i] >= self.env._max_episode_steps)
+                if self.flag_time_limit and self._len[i] >= self.env._max_episode_steps and not self._ended_by_bounds(i, done_np):
+                    infos[i]["TimeLimit.truncated"] = True
                 if term_np is not None:
                     infos[i]["terminal_observation"] = term_np[j]
                 if self._csv is not None:
@@ -221,6 +226,12 @@ class Sb3VecEnv:
             self._ret[idx] = 0
             self._len[idx] = 0
         return obs_np, rew_np, done_np, infos
+
+    def _ended_by_bounds(self, i, done_np):
+        """True when environment ``i`` terminated by leaving the domain (legacy envs: verySimpleAuv.py:332-345) rather
+        than by the step limit; the rov envs have no bounds termination."""
+        oob = getattr(self.env, "out_of_bounds", None)
+        return bool(oob[i]) if oob is not None else False
 
     def step(self, actions):
         self.step_async(actions)

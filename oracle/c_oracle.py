@@ -22,7 +22,12 @@ class OrcRov6Params(C.Structure):
 
 
 class OrcPid6(C.Structure):
-    _fields_ = [("eOld", _d * 6), ("eInt", _d * 6), ("tOld", _d), ("has_old", C.c_int)]
+    _fields_ = [("eOld", _d * 6), ("eInt", _d * 6), ("tOld", _d), ("margin", _d), ("has_old", C.c_int)]
+
+
+# numpy view of an (OrcPid6 * n) array: lets the tests read / overwrite the controller state of all environments at once
+PID6_DTYPE = np.dtype([("eOld", "f8", 6), ("eInt", "f8", 6), ("tOld", "f8"), ("margin", "f8"), ("has_old", "i4")], align=True)
+assert PID6_DTYPE.itemsize == C.sizeof(OrcPid6)
 
 
 class OrcRov6Env(C.Structure):
@@ -102,6 +107,8 @@ class Rov6EnvC:
         self.set_point = np.ascontiguousarray(self._np.set_point)
         self.path = np.ascontiguousarray(self._np.path)
         self.ctrl = (OrcPid6 * n)()
+        self.ctrl_np = np.frombuffer(self.ctrl, dtype=PID6_DTYPE)   # shares memory with self.ctrl
+        self.ctrl_np["margin"] = np.inf
         self.i_step = np.zeros(n, dtype=np.int32)
         self.time = np.zeros(n)
         self.episode = np.zeros(n, dtype=np.uint32)
@@ -110,11 +117,12 @@ class Rov6EnvC:
         self.term_obs = np.zeros((n, 9))
         self.aux = np.zeros((n, 14))
         self.mincos = np.ones(n)  # running min |cos(theta)| over all RK4 stages (conditioning diagnostic)
+        self.dbmargin = np.full(n, np.inf)  # running min relative distance of a thruster demand from the dead-band edge
         return self.obs.copy()
 
     def step(self, action):
         action = np.ascontiguousarray(action, dtype=np.float64)
         self.lib.orc_rov6_step(C.byref(self.ps), C.byref(self.cfg), C.c_long(self.n), _p(self.state), _p(action),
                                _p(self.set_point), _p(self.path), self.ctrl, _p(self.i_step), _p(self.time), _p(self.episode),
-                               _p(self.obs), _p(self.done), _p(self.term_obs), _p(self.aux), _p(self.mincos))
+                               _p(self.obs), _p(self.done), _p(self.term_obs), _p(self.aux), _p(self.mincos), _p(self.dbmargin))
         return self.obs, np.zeros(self.n), self.done.astype(bool), {"terminal_observation": self.term_obs}

@@ -100,9 +100,17 @@ static void allocate_thrust(const OrcRov6Params* p, const double* ang, const dou
     }
 }
 
+/* NOT part of the algorithm - conditioning diagnostic for the parity tests: the smallest relative distance of a thruster
+ * demand from the dead-band edge (| |rpm| - 300 | / 300) seen by the calling thread since it was last reset.  The thrust
+ * jumps from 0 to 0.29 N there, so an environment that comes within rounding distance of the edge cannot agree
+ * between two precisions. */
+static _Thread_local double g_dbmargin = 1e300;
+
 /* 6DoF.py:271-275 */
 static double limit_rpm(double x) {
     double r = fmax(-3500., fmin(3500., x));
+    const double m = fabs(fabs(r) - 300.) / 300.;
+    if (m < g_dbmargin) g_dbmargin = m;
     if (fabs(r) < 300) r = 0.;
     return r;
 }
@@ -195,7 +203,10 @@ static void solve6(double A[6][6], double* b) {
 }
 
 /* controller state, 6DoF.py:37-41 */
-typedef struct OrcPid6 { double eOld[6], eInt[6], tOld; int has_old; } OrcPid6;
+/* margin is NOT part of the algorithm: a conditioning diagnostic for the parity tests.  It keeps the smallest non-zero
+ * |e - eOld| seen by a call with t - tOld < 1e-9, where dedt = (e - eOld) / 1e-9 turns the sign of that difference
+ * into a saturated demand (RK4 stages 1 and 3) - the distance of the environment from a sign flip. */
+typedef struct OrcPid6 { double eOld[6], eInt[6], tOld, margin; int has_old; } OrcPid6;
 
 static const double PID_WINDUP[6] = {2., 2., 2., 90. / 180. * M_PI, 90. / 180. * M_PI, 90. / 180. * M_PI};
 static const double PID_MAX[6] = {50., 50., 50., 1., 1., 2.};
@@ -210,6 +221,12 @@ static void pid_control(OrcPid6* c, const double* sp, const double* pose, double
     e[5] = orc_angle_error(sp[5], pose[5]);
     if (!c->has_old) { memcpy(c->eOld, e, sizeof(e)); c->has_old = 1; }
     const double dtc = t - c->tOld;
+    if (dtc < 1e-9) {
+        for (int k = 0; k < 6; ++k) {
+            const double d = fabs(e[k] - c->eOld[k]);
+            if (d > 0. && d < c->margin) c->margin = d;
+        }
+    }
     for (int k = 0; k < 6; ++k) {
         const double dedt = (e[k] - c->eOld[k]) / fmax(1e-9, dtc);
         c->eInt[k] += 0.5 * (c->eOld[k] + e[k]) * dtc;
@@ -286,10 +303,11 @@ typedef struct OrcRov6Env {
  * state [n][12], action [n][8|6], setpoint [n][6], path [n][6], ctrl [n], istep [n], time [n],
  * episode [n] -> obs [n][9], done [n], term_obs [n][9] (nullable), aux [n][14] (nullable).
  * mincos [n] (nullable, in/out): running minimum of |cos(theta)| over every RK4 stage - a conditioning
- * diagnostic for the tests (distance from the 1/cos(theta) pole of J2), not part of the algorithm. */
+ * diagnostic for the tests (distance from the 1/cos(theta) pole of J2), not part of the algorithm.
+ * dbmargin [n] (nullable, in/out): running minimum of the dead-band distance (see g_dbmargin), likewise. */
 void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* state, const double* action, double* setpoint,
                    double* path, OrcPid6* ctrl, int32_t* istep, double* time, uint32_t* episode, double* obs, uint8_t* done,
-                   double* term_obs, double* aux, double* mincos) {
+                   double* term_obs, double* aux, double* mincos, double* dbmargin) {
     const int na = e->mode == 0 ? 8 : 6;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(e->threads > 0 ? e->threads : omp_get_max_threads())
@@ -302,6 +320,7 @@ void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* 
         double gcf[6] = {0, 0, 0, 0, 0, 0}, cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         istep[i] += 1;
         time[i] += e->dt;
+        g_dbmargin = 1e300;
         if (e->mode == 2 && !e->fixed_sp) { /* 6DoF.py:545-552 */
             for (int k = 0; k < 3; ++k) {
                 sp[k] = act[k] * (2. * p->Length) + y[k];
@@ -325,6 +344,7 @@ void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* 
             }
             for (int k = 0; k < 12; ++k) y[k] = y[k] + (h / 6.0) * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
         }
+        if (dbmargin && g_dbmargin < dbmargin[i]) dbmargin[i] = g_dbmargin;
         for (int k = 3; k < 6; ++k) y[k] = pymod(y[k], TWO_PI); /* 6DoF.py:560 */
         observe(p, y, path + 6 * i, sp, obs + 9 * i);
         done[i] = istep[i] >= e->max_steps;
@@ -340,7 +360,7 @@ void orc_rov6_step(const OrcRov6Params* p, const OrcRov6Env* e, long n, double* 
                 for (int k = 0; k < 6; ++k) path[6 * i + k] = (u[k] - 0.5) * 10.;
                 for (int k = 0; k < 3; ++k) { sp[k] = path[6 * i + k]; sp[3 + k] = u[6 + k] * TWO_PI; }
             }
-            if (c) memset(c, 0, sizeof(*c));
+            if (c) { const double mg = c->margin; memset(c, 0, sizeof(*c)); c->margin = mg; }
             observe(p, y, path + 6 * i, sp, obs + 9 * i);
         }
     }

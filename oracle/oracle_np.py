@@ -189,6 +189,17 @@ PID6_KI = np.array([2., 2., 2., 0.1, 0.1, 0.2])
 PID6_KD = np.array([20., 20., 20., 5., 5., 0.65])
 
 
+def _track_margin(ctrl, e, e_old, dtc):
+    """NOT part of the algorithm - a conditioning diagnostic for the parity tests, kept only when the caller put a
+    "margin" array into ``ctrl``: the smallest non-zero |e - eOld| seen by a call with t - tOld < 1e-9, where
+    dedt = (e - eOld) / 1e-9 turns the SIGN of that difference into a saturated demand (RK4 stages 1 and 3)."""
+    if "margin" not in ctrl:
+        return
+    d = np.abs(e - e_old)
+    d = np.where((d > 0.) & (dtc < 1e-9)[:, None], d, np.inf).min(axis=1)
+    ctrl["margin"] = np.minimum(ctrl["margin"], d)
+
+
 def pid6_new_state(n):
     """6DoF.py:37-41: eOld=None, eInt=0, tOld=0."""
     return {"eOld": np.zeros((n, 6)), "has_old": np.zeros(n, dtype=bool),
@@ -209,6 +220,7 @@ def pid6_control(ctrl, set_point, pose, t):
     e[:, 5] = angle_error(set_point[:, 5], pose[:, 5])
     e_old = np.where(ctrl["has_old"][:, None], ctrl["eOld"], e)
     dtc = t - ctrl["tOld"]
+    _track_margin(ctrl, e, e_old, dtc)
     dedt = (e - e_old) / np.maximum(1e-9, dtc)[:, None]
     e_int = ctrl["eInt"] + 0.5 * (e_old + e) * dtc[:, None]
     e_int = np.where(np.abs(e) > PID6_WINDUP, 0., e_int)
@@ -246,9 +258,18 @@ def allocate_thrust6(p, axes, gcf):
     return np.sign(cv) * np.sqrt(np.abs(cv) / (p.rho_f * p.D_thruster ** 4. * p.Kt_thruster)) * 60.
 
 
+# NOT part of the algorithm - conditioning diagnostic for the parity tests.  A test may set DIAG["dbmargin"] to an
+# array [n] of +inf; limit_rpm then keeps in it the smallest relative distance | |rpm| - 300 | / 300 of a thruster demand
+# from the dead-band edge, where the thrust jumps from 0 to 0.29 N (an environment that comes within rounding distance
+# of the edge cannot agree between two precisions).
+DIAG = {"dbmargin": None}
+
+
 def limit_rpm(rpm):
     """6DoF.py:271-275: saturate at +-3500, zero inside the 300 rpm deadband."""
     r = np.maximum(-3500., np.minimum(3500., rpm))
+    if DIAG["dbmargin"] is not None and np.ndim(r) == 2 and r.shape[0] == DIAG["dbmargin"].shape[0]:
+        DIAG["dbmargin"] = np.minimum(DIAG["dbmargin"], (np.abs(np.abs(r) - 300.) / 300.).min(axis=1))
     return np.where(np.abs(r) < 300, 0., r)
 
 
@@ -613,6 +634,7 @@ def pid3_control(ctrl, set_point, pose, t):
     e = np.stack([set_point[:, 0] - pose[:, 0], set_point[:, 1] - pose[:, 1], angle_error(set_point[:, 2], pose[:, 2])], axis=1)
     e_old = np.where(ctrl["has_old"][:, None], ctrl["eOld"], e)
     dtc = t - ctrl["tOld"]
+    _track_margin(ctrl, e, e_old, dtc)
     dedt = (e - e_old) / np.maximum(1e-9, dtc)[:, None]
     e_int = ctrl["eInt"] + 0.5 * (e_old + e) * dtc[:, None]
     e_int = np.where(np.abs(e) > PID3_WINDUP, 0., e_int)

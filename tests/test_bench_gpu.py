@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_bench_line_contract_on_a_small_batch():
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--envs", "8192", "--cpu-steps", "5"],
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--envs", "8192", "--cpu-steps", "5", "--extra-steps", "10"],
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
@@ -30,3 +30,7 @@ def test_bench_line_contract_on_a_small_batch():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8192 * 8 * 4 and e["d2h_bytes_per_step"] == 8192 * (9 * 4 + 4 + 1)
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+    assert c["as_shipped_rk45_pid_port_one_core"] > 0 and c["legacy_auv_step_port_one_core"] > 0
+    r5 = d["extra"]["config5_rollout"]   # config 5 rides along at every N
+    assert r5["value"] > 0 and 0 < r5["env_share"] < 1
+    assert r["executed_flop_per_env_step"] > 0

@@ -195,32 +195,41 @@ def test_trajectory_4096_envs_1000_steps_fp32_vs_oracle():
     the oracle sees the fp32-rounded actions): tolerance 1e-4 on the state scaled by 1 + |ref| (BASELINE north_star).
 
     Conditioning as in the fp64 test, with a wider band because fp32 round-off is 1e9 times larger: an environment is
-    compared up to its first RK4 stage with |cos(theta)| < 0.3 (inside, 1/cos(theta) amplifies a 6e-8 rounding of
-    theta by > 10 per stage).  Measured on B200 (the same loop, printing the error distribution by conditioning): worst 5.5e-5 outside the band over all
-    1000 steps, median over all 4096 envs 1.2e-5; 3 of the 2090 envs that only stay outside |cos| < 0.1 reach 4e-4."""
+    compared up to its first RK4 stage with |cos(theta)| < band (inside, 1/cos(theta) amplifies a 6e-8 rounding of
+    theta).  Full-throttle random thrusters tumble the vehicles, so the set that never enters a band shrinks with time -
+    that is the workload, not the kernel (the oracle alone decides it): 75 % / 23 % / 5.4 % of the 4096 environments
+    stay outside |cos| < 0.3 for 100 / 500 / 1000 steps, 94 % / 72 % / 51 % outside |cos| < 0.1.  Both fractions are
+    asserted, with 1e-4 for the first band and 1e-3 for the second (measured on B200: 5.5e-5 and 4e-4).  Every
+    environment, tumbling or not, is covered step by step by test_parity_modes_gpu.py::test_rov6_one_step_local_error_all_envs."""
     from oracle import c_oracle as c
-    n, steps, band = 4096, 1000, 0.3
+    n, steps = 4096, 1000
     gen = torch.Generator(device="cpu").manual_seed(1234)
     env = make_env(n, "rpm", dtype=torch.float32)
     env.reset(initialSetpoint=np.zeros(6))
     ref = c.Rov6EnvC(n, mode=o.MODE_RPM, max_steps=10 ** 9)
     ref.reset(initial_setpoint=np.zeros(6))
-    worst, compared = 0.0, 0
+    worst = {0.3: 0.0, 0.1: 0.0}
+    frac = {}
     for k in range(steps):
         a = ((torch.rand((n, 8), generator=gen, dtype=torch.float64) * 2 - 1) * 3500.0).to(torch.float32)
         env.step(a.to(DEV))
         ref.step(a.to(torch.float64).numpy())
         if k % 10 == 9 or k == steps - 1:
-            good = ref.mincos >= band
             d = np.abs(env.systemState.cpu().numpy().astype(np.float64) - ref.state)
             d[:, 3:6] = np.abs((d[:, 3:6] + np.pi) % (2 * np.pi) - np.pi)
-            worst = max(worst, (d / (1.0 + np.abs(ref.state)))[good].max())
-            compared += int(good.sum())
-            if k == 99:
-                assert good.sum() >= 0.5 * n, good.sum()       # most environments are compared for at least 100 steps
-    print("env-checks compared: %d; envs outside the band for all %d steps: %d; worst scaled error %.3e" % (compared, steps, good.sum(), worst))
-    assert good.sum() >= 100
-    assert worst < 1e-4, worst
+            d = (d / (1.0 + np.abs(ref.state))).max(axis=1)
+            for band in worst:
+                good = ref.mincos >= band
+                worst[band] = max(worst[band], d[good].max())
+                if k + 1 in (100, 500, 1000):
+                    frac[(band, k + 1)] = float(good.mean())
+    print("fp32 rpm trajectories: fraction of %d envs compared for 100 / 500 / 1000 steps and worst scaled error - outside |cos| < 0.3: "
+          "%.3f / %.3f / %.3f, %.3e; outside |cos| < 0.1: %.3f / %.3f / %.3f, %.3e" %
+          (n, frac[(0.3, 100)], frac[(0.3, 500)], frac[(0.3, 1000)], worst[0.3], frac[(0.1, 100)], frac[(0.1, 500)], frac[(0.1, 1000)], worst[0.1]))
+    assert frac[(0.3, 100)] >= 0.70 and frac[(0.3, 500)] >= 0.20 and frac[(0.3, 1000)] >= 0.045, frac
+    assert frac[(0.1, 100)] >= 0.90 and frac[(0.1, 500)] >= 0.65 and frac[(0.1, 1000)] >= 0.45, frac
+    assert worst[0.3] < 1e-4, worst
+    assert worst[0.1] < 1e-3, worst
 
 
 def test_trajectory_fp32_within_1e4():
@@ -371,26 +380,3 @@ def test_two_envs_per_thread_kernel_matches_one_env_kernel_bitwise(monkeypatch):
                 nn = lambda t: torch.nan_to_num(t, nan=12345.0)   # ctrl[0] = NaN marks a fresh controller
                 assert torch.equal(packed._state, single._state) and torch.equal(nn(packed._ctrl), nn(single._ctrl)), (mode, fast, k)
             assert packed.episode_stats() == single.episode_stats()
-
-
-def test_warp_specialised_kernel_matches_plain_kernel_bitwise(monkeypatch):
-    """The opt-in warp-specialised persistent variant (csrc/rov6_ws_kernel.cuh: IO warps + compute warps handing
-    tiles over through mbarriers, MVRL_WS=1) runs the same arithmetic per environment as the plain fused kernel:
-    bitwise equal observations, dones, states, way-points, counters and statistics, with auto-reset, for batch sizes
-    that leave lanes, warps and whole CTAs of the persistent grid empty."""
-    kw = dict(action_mode="rpm", dtype=torch.float32, device=DEV, maxSteps=3, auto_reset=True, seed=5)
-    for n in (1, 65, 777, 100001):
-        rng = np.random.default_rng(n)
-        acts = torch.as_tensor(rng.uniform(-3500, 3500, (7, n, 8)), dtype=torch.float32, device=DEV)
-        monkeypatch.setenv("MVRL_WS", "0")
-        plain = BlueROV2Heavy6DoFVecEnv(n, **kw)
-        monkeypatch.setenv("MVRL_WS", "1")
-        ws = BlueROV2Heavy6DoFVecEnv(n, **kw)
-        assert torch.equal(plain.reset(), ws.reset())
-        for k in range(acts.shape[0]):
-            op, _, dp, ip = plain.step(acts[k])
-            ow, _, dw, iw = ws.step(acts[k])
-            assert torch.equal(op, ow) and torch.equal(dp, dw), (n, k)
-            assert torch.equal(ip["terminal_observation"], iw["terminal_observation"]), (n, k)
-            assert torch.equal(plain._state, ws._state) and torch.equal(plain._path, ws._path) and torch.equal(plain._istep, ws._istep), (n, k)
-        assert plain.episode_stats() == ws.episode_stats()

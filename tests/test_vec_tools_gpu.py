@@ -92,11 +92,17 @@ def test_sb3_vecenv_protocol_and_monitor_csv(tmp_path):
         if (k + 1) % 4 == 0:
             assert done.all()
             assert all(i["episode"]["l"] == 4 and i["episode"]["r"] == 0.0 and i["terminal_observation"].shape == (9,) for i in infos)
-            assert all(i["TimeLimit.truncated"] for i in infos)
+            assert all("TimeLimit.truncated" not in i for i in infos)   # like the reference envs: no TimeLimit wrapper upstream
             n_ep += 16
         else:
             assert not done.any() and all(i == {} for i in infos)
     venv.close()
+    flagged = vec_tools.Sb3VecEnv(BlueROV2Heavy6DoFVecEnv(4, action_mode="setpoint", dtype=torch.float32, device=DEV, maxSteps=2, auto_reset=True),
+                                  flag_time_limit=True)
+    flagged.reset()
+    for k in range(2):
+        _, _, done, infos = flagged.step(np.zeros((4, 6), dtype=np.float32))
+    assert done.all() and all(i["TimeLimit.truncated"] is True for i in infos)   # opt-in
     lines = open(str(tmp_path / "run" / "agent_0.monitor.csv")).read().splitlines()
     assert lines[0].startswith("#{") and lines[1] == "r,l,t" and len(lines) == 2 + n_ep
     assert venv.env_is_wrapped(object) == [False] * 16 and venv.get_attr("num_envs") == [16] * 16
