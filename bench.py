@@ -468,57 +468,75 @@ def rov3_leg(dev, rank, world, n, mode, n_sub=N_SUB, steps=50, warmup=5, clocks=
             "action_mode": mode, "n_sub": n_sub, "clocks": clk, "episode_stats": env.episode_stats()}
 
 
-def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, clocks=False):
-    """Config 5: rollout collection over the 6DoF env in the reference's Gym semantics (PID set-point actions): policy MLP
-    9-128-128-128-6 (GELU, arch of legacy/main_00_sbl.py:100-105) + Gaussian head in PyTorch on the feature-major observation
-    buffer, T-step rollouts replayed as one CUDA graph, episode statistics all-reduced once per rollout (K5, NCCL when N > 1)."""
+def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, clocks=False, policy="fused"):
+    """Config 5: rollout collection over the 6DoF env in the reference's Gym semantics (PID set-point actions) with the
+    policy of legacy/main_00_sbl.py:100-105 (MLP 9-128-128-128-6, GELU) + Gaussian head; T-step rollouts replayed as one
+    CUDA graph, episode statistics all-reduced once per rollout (K5, NCCL when N > 1).
+    policy = "fused": the actor is ONE tensor-core kernel (mvrl_policy_act) on the env's own buffers and the env writes
+    observation / reward / done straight into the rollout buffers, so a rollout step is two launches.
+    policy = "torch": the same network as PyTorch library calls (cuBLASLt TF32 GEMMs with fused bias + GELU, elementwise
+    sampling kernels) - the baseline the fused actor replaces."""
     import torch
-    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv, MlpGaussianPolicy
     torch.backends.cuda.matmul.allow_tf32 = True
     env = BlueROV2Heavy6DoFVecEnv(n, action_mode="setpoint", dtype=torch.float32, device=dev, n_sub=n_sub, seed=1234,
                                   env_id0=rank * n, auto_reset=True, record_terminal_obs=False)
     env.reset()
-    torch.manual_seed(1234 + rank)
-    dims = [9, 128, 128, 128, 6]
-    Ws = [torch.randn(dims[i + 1], dims[i], device=dev) / dims[i] ** 0.5 for i in range(4)]
-    log_std = torch.full((6, 1), -0.5, device=dev)
+    pol = MlpGaussianPolicy(9, 6, device=dev, seed=1234)
     ld = env.ld
-    buf_obs = torch.empty((T, 9, ld), device=dev)
+    buf_obs = torch.empty((T + 1, 9, ld), device=dev)
     buf_act = torch.empty((T, 6, ld), device=dev)
     buf_logp = torch.empty((T, ld), device=dev)
     buf_rew = torch.empty((T, ld), device=dev)
     buf_done = torch.empty((T, ld), dtype=torch.uint8, device=dev)
-    Wt = [w.T.contiguous() for w in Ws]         # [in, out]
-    b1 = [torch.zeros(dims[i + 1], device=dev) for i in range(4)]
-    obs_nk = env._obs.T                          # [ld, 9] strided view of the SoA observation buffer: cuBLAS reads it in place
+    own = (env._bufs.obs, env._bufs.action, env._bufs.reward, env._bufs.done)
 
-    def policy(x_nk):         # batch-major activations [N, k]; bias + GELU fused into the GEMM epilogue (cuBLASLt)
-        h = x_nk
-        for i in range(3):
-            h = torch._addmm_activation(b1[i], h, Wt[i], use_gelu=True)
-        return torch.tanh(torch.addmm(b1[3], h, Wt[3]))      # [N, 6]
+    if policy == "fused":
+        buf_obs[0].copy_(env._obs)
 
-    std = log_std.exp().reshape(1, 6)
-    logp_const = float(-log_std.sum())
+        def policy_step(t):
+            pol.act_into(buf_obs[t], buf_act[t], n, logp=buf_logp[t], env_id0=rank * n, step=t)
 
-    def policy_step(t):
-        buf_obs[t].copy_(env._obs)
-        mean = policy(obs_nk)
-        eps = torch.randn_like(mean)
-        act = torch.addcmul(mean, eps, std).clamp_(-1., 1.)
-        buf_logp[t].copy_((eps * eps).sum(1).mul_(-0.5).add_(logp_const))
-        buf_act[t].copy_(act.T)             # back to the env's feature-major action layout
+        def env_step(t):   # the step kernel reads the actor's output and writes the next rollout row: no copies
+            env._bufs.action, env._bufs.obs = buf_act[t].data_ptr(), buf_obs[t + 1].data_ptr()
+            env._bufs.reward, env._bufs.done = buf_rew[t].data_ptr(), buf_done[t].data_ptr()
+            env.step_async()
 
-    def env_step(t):
-        env._bufs.action = buf_act[t].data_ptr()
-        env.step_async()
-        buf_rew[t].copy_(env._reward)
-        buf_done[t].copy_(env._done)
+        def rollout():
+            for t in range(T):
+                policy_step(t)
+                env_step(t)
+            buf_obs[0].copy_(buf_obs[T])   # the next rollout starts where this one ended
+        launches_per_step = 2
+    else:
+        Wt = [w.to(dev).T.contiguous() for w in pol.weights]         # [in, out]
+        b1 = [b.to(dev) for b in pol.biases]
+        obs_nk = env._obs.T                          # [ld, 9] strided view of the SoA observation buffer: cuBLAS reads it in place
+        std = pol.log_std.exp().reshape(1, 6).to(dev)
+        logp_const = pol.logp_const
 
-    def rollout():
-        for t in range(T):
-            policy_step(t)
-            env_step(t)
+        def policy_step(t):
+            buf_obs[t].copy_(env._obs)
+            h = obs_nk
+            for i in range(3):    # batch-major activations [N, k]; bias + GELU fused into the GEMM epilogue (cuBLASLt)
+                h = torch._addmm_activation(b1[i], h, Wt[i], use_gelu=True)
+            mean = torch.tanh(torch.addmm(b1[3], h, Wt[3]))
+            eps = torch.randn_like(mean)
+            act = torch.addcmul(mean, eps, std).clamp_(-1., 1.)
+            buf_logp[t].copy_((eps * eps).sum(1).mul_(-0.5).add_(logp_const))
+            buf_act[t].copy_(act.T)             # back to the env's feature-major action layout
+
+        def env_step(t):
+            env._bufs.action = buf_act[t].data_ptr()
+            env.step_async()
+            buf_rew[t].copy_(env._reward)
+            buf_done[t].copy_(env._done)
+
+        def rollout():
+            for t in range(T):
+                policy_step(t)
+                env_step(t)
+        launches_per_step = None
     rollout()
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
@@ -534,7 +552,7 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
         graph.replay()
         holder["s"] = env.episode_stats()     # K5: device accumulators -> all-reduce (NCCL) -> host, once per rollout
     ms, clk = timed_launches(dev, world, one_rollout, rollouts, 1, graph=False, clocks=clocks)
-    # share of the env step: the same T env steps alone (policy buffers as actions), as one graph
+    # share of the env step: the same T env steps alone (the actor's last outputs as actions), as one graph
     g2 = torch.cuda.CUDAGraph()
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
@@ -543,13 +561,17 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
                 env_step(t)
     torch.cuda.current_stream(dev).wait_stream(side)
     ms_env, _ = timed_launches(dev, world, lambda k: g2.replay(), rollouts, 1, graph=False)
-    env._bufs.action = env._action.data_ptr()
+    env._bufs.obs, env._bufs.action, env._bufs.reward, env._bufs.done = own
     per_step = ms / (rollouts * T)
+    dims = [9, 128, 128, 128, 6]
     return {"value": n * T * rollouts / (ms * 1e-3), "unit": UNIT + " per GPU (policy included)", "ms_per_step": per_step, "envs_per_gpu": n,
-            "rollout_len": T, "rollouts": rollouts, "env_share": (ms_env / (rollouts * T)) / per_step,
+            "rollout_len": T, "rollouts": rollouts, "policy_impl": policy, "launches_per_step": launches_per_step,
+            "env_share": (ms_env / (rollouts * T)) / per_step,
             "env_us_per_step": 1e3 * ms_env / (rollouts * T), "policy_and_bookkeeping_us_per_step": 1e3 * (per_step - ms_env / (rollouts * T)),
             "flop_per_env_step": {"env": flop_per_env_step("setpoint", n_sub), "policy": 2 * sum(dims[i] * dims[i + 1] for i in range(4))},
-            "policy": "MLP 9-128-128-128-6 GELU + Gaussian head, PyTorch (cuBLASLt TF32 GEMMs with fused bias + GELU): library code by BASELINE's definition of config 5",
+            "policy": ("MLP 9-128-128-128-6 GELU + Gaussian head as one kernel: mma.sync bf16 (fp32 accumulate), activations in registers, "
+                       "weights in shared memory, Philox sampling (csrc/mvrl_policy.cu)") if policy == "fused" else
+                      "MLP 9-128-128-128-6 GELU + Gaussian head, PyTorch (cuBLASLt TF32 GEMMs with fused bias + GELU): library code",
             "stats_allreduce": "episode statistics (8 doubles) all-reduced once per rollout, inside the timed region" if world > 1 else "single rank: no collective",
             "clocks": clk, "episode_stats": holder.get("s")}
 
@@ -598,7 +620,7 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = _max_over_ranks(time.perf_counter() - w0, dev, world)
     e2e_value = n_total * e2e_steps / e2e_s
     h2d = n * na * w
-    d2h = n * (9 * w + w + 1)
+    d2h = n * (9 * w + 1)     # obs + done; the reward is identically 0 and is not shipped (the host array is zero-filled once)
     e2e_pieces = _lib.load().mvrl_host_chunk_count(n, args.e2e_chunks)
     del env, acts, h_act, leg["env"], leg["acts"]
 
@@ -634,7 +656,9 @@ def run_ours(args, rank, local_rank, world):
             extra["config4_auv_262144_envs"] = auv_leg(dev, rank, world, 262144, 4 * xs, xw)
             extra["rov3_setpoint_f32"] = rov3_leg(dev, rank, world, big, "setpoint", steps=xs, warmup=xw)
             extra["rov3_rpm_f32"] = rov3_leg(dev, rank, world, big, "rpm", steps=xs, warmup=xw)
-        extra["config5_rollout"] = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2)
+        extra["config5_rollout"] = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="fused")
+        tl = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="torch")
+        extra["config5_rollout"]["pytorch_policy_baseline"] = {k: tl[k] for k in ("value", "ms_per_step", "env_share", "policy_and_bookkeeping_us_per_step", "policy")}
         if world > 1:
             extra["config5_rollout"]["value_all_gpus"] = extra["config5_rollout"]["value"] * world
 
@@ -691,7 +715,7 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "chunks": e2e_pieces, "host_numa_node": numa_node, "gpu_launches_per_step": 3 * e2e_pieces,
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
-                                "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, reward + done stored into the pinned host arrays by the transpose kernel)"},
+                                "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, done stored into the pinned host array by the transpose kernel; the always-zero reward does not travel)"},
                 "gpu_launches": args.steps, "clocks": leg.get("clocks"), "episode_stats": leg.get("episode_stats")}
         if strong_leg is not None:
             line["strong"] = strong_leg
@@ -724,11 +748,12 @@ def run_secondary(args, rank, local_rank, world):
     else:
         n = args.envs if args.envs != ENVS_PER_GPU else 131072
         rollouts = max(2, args.steps // args.rollout_len)
-        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True)
-        metric, dtype = "6DoF rollout collection env-steps/sec (policy included)", "f32 (policy matmuls TF32)"
+        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True, policy=args.policy)
+        metric, dtype = "6DoF rollout collection env-steps/sec (policy included)", "f32 env; policy bf16 operands / fp32 accumulate (fused) or TF32 (torch)"
         cfg = {"workload": "rollout: 6DoF set-point env + MLP 9-128-128-128-6 GELU Gaussian policy, %d envs/GPU, %d-step rollouts, "
                            "nSub=%d, CUDA-graph replay, stats all-reduce per rollout" % (n, args.rollout_len, args.n_sub)}
-        extra = {k: r[k] for k in ("env_share", "env_us_per_step", "policy_and_bookkeeping_us_per_step", "flop_per_env_step", "policy", "stats_allreduce")}
+        extra = {k: r[k] for k in ("env_share", "env_us_per_step", "policy_and_bookkeeping_us_per_step", "flop_per_env_step", "policy", "policy_impl",
+                                   "launches_per_step", "stats_allreduce")}
         launches = rollouts * args.rollout_len
     if rank == 0:
         line = {"metric": metric, "value": world * r["value"], "unit": UNIT, "n_gpus": world, "steps": r.get("steps", launches), "warmup": args.warmup,
@@ -760,6 +785,7 @@ def main():
                     help="rov6 = BASELINE config 3 (the metric); rov3 = the 3DoF env at scale; auv = config 4; rollout = config 5")
     ap.add_argument("--field", default="modes", choices=["modes", "noise"], help="auv: synthetic turbulence stand-in")
     ap.add_argument("--rollout-len", type=int, default=128)
+    ap.add_argument("--policy", default="fused", choices=["fused", "torch"], help="rollout: the fused tensor-core actor or the PyTorch baseline")
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
     ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
     ap.add_argument("--bind-numa", type=int, default=1, help="1: bind each rank to the CPUs of its GPU's NUMA node (host buffers of the e2e leg)")

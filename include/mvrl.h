@@ -169,9 +169,11 @@ MVRL_API int mvrl_rov6_step_range(MvrlRov6* h, int64_t first, int64_t n, int64_t
  * T [n] (nullable), done_host [n] (nullable) out.  Pinned host memory is needed for the copies to overlap.
  * The batch is cut into `chunks` equal pieces (0: the default - 8, fewer for batches under 512 Ki environments); upload, transpose to SoA, fused step, transpose
  * back and download of different pieces overlap on streams owned by the handle (PCIe is full duplex).  The
- * observations travel by copy engine; reward and done flags (5 B per environment) are stored straight into
- * reward_host / done_host by the transpose kernel when those arrays are pinned, so that the download engine has
- * one copy per piece to do (pageable arrays: copied like the observations).
+ * observations travel by copy engine; the done flags (1 B per environment) are stored straight into done_host by
+ * the transpose kernel when that array is pinned, so that the download engine has one copy per piece to do (a
+ * pageable array is copied like the observations).  The reward of this env is identically 0 (6DoF.py:575) and does
+ * NOT travel: reward_host is zero-filled on the host side - on every call with chunks < 0, and when the pipeline for
+ * this set of pointers is captured otherwise; a caller that scribbles on it between calls must clear it again.
  * The whole pipeline is captured into a CUDA graph once per distinct set of pointers (4 cached) and
  * replayed with one launch; chunks < 0 queues |chunks| pieces directly on the streams instead.
  * Device staging buffers are allocated on first use.  Starts after the work queued on `stream` and returns
@@ -333,6 +335,25 @@ MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t ld, const v
                                        const void* reward, const uint8_t* done, void* buf_obs, void* buf_next_obs, void* buf_act,
                                        void* buf_reward, uint8_t* buf_done, int64_t buffer_size, int64_t pos, int n_transforms,
                                        mvrl_stream_t stream);
+
+/* ------------------------------------------------------------ rollout actor -- */
+/* The policy the reference trains with SB3 (tag_00.../main_00_sbl.py:100-105: MlpPolicy, net_arch [128, 128, 128], GELU)
+ * and its Gaussian action head, as one tensor-core kernel on the env's own buffers - BASELINE.json config 5 (rollout
+ * collection): obs float [obs_dim][ld] (the step kernels' structure-of-arrays observation buffer, read in place) ->
+ * act float [act_dim][ld] (the structure-of-arrays action buffer the step kernels read).  mean = tanh(W4 gelu(W3 gelu(W2
+ * gelu(W1 obs + b1) + b2) + b3) + b4), act = clip(mean + exp(log_std) * eps, -1, 1), eps ~ N(0, 1) from Philox keyed on
+ * (seed, env_id0 + i, step) - independent of how the batch is sharded; logp (nullable) [n] = -0.5 sum eps^2 - sum log_std;
+ * mean / eps (nullable) [act_dim][ld] for the learner and the tests; deterministic != 0 returns the mean (SB3
+ * predict(obs, deterministic=True)).  Operands are bf16 (fp32 accumulate), GELU in its tanh form (torch gelu(approximate=
+ * "tanh")).  fp32 only; obs_dim <= 16, act_dim <= 8, hidden width 128.  set_weights takes HOST arrays in torch.nn.Linear layout
+ * (W [out][in]) and synchronises; act launches on the caller's stream and does not synchronise. */
+typedef struct MvrlPolicy MvrlPolicy;
+MVRL_API int mvrl_policy_create(MvrlPolicy** out, int device, int obs_dim, int act_dim);
+MVRL_API int mvrl_policy_destroy(MvrlPolicy* h);
+MVRL_API int mvrl_policy_set_weights(MvrlPolicy* h, const float* W1, const float* b1, const float* W2, const float* b2,
+                                     const float* W3, const float* b3, const float* W4, const float* b4, const float* log_std);
+MVRL_API int mvrl_policy_act(MvrlPolicy* h, int64_t n, int64_t ld, const float* obs, float* act, float* logp, float* mean,
+                             float* eps, uint64_t seed, uint64_t env_id0, uint32_t step, int deterministic, mvrl_stream_t stream);
 
 /* ------------------------------------------------------------ calibration -- */
 /* K6: measured FMA throughput of the FP32 / FP64 pipe in TFLOP/s (2 flop per FMA,

@@ -124,6 +124,10 @@ PROTOTYPES = {
     "mvrl_flow_interp": (_int, [_int, _vp, _int, _int, _int, _int, _d, _d, _d, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mvrl_replay_add_symmetric": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "mvrl_flow_scale": (_int, [_int, _i64, _vp, _vp, _int, _d, _d, _vp]),
+    "mvrl_policy_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
+    "mvrl_policy_destroy": (_int, [_vp]),
+    "mvrl_policy_set_weights": (_int, [_vp] + [_vp] * 9),
+    "mvrl_policy_act": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _int, _vp]),
 }
 
 _lib = None

@@ -501,9 +501,13 @@ static int enqueue_host_step(MvrlRov6* h, int64_t n, int64_t ld, const MvrlRov6B
     const int n_act = h->c.action_mode == MVRL_ACT_RPM ? 8 : 6;
     int64_t bounds[MvrlRov6::kMaxChunks + 1];
     const int n_chunks = host_chunk_plan(n, chunks, bounds);
-    // reward / done: written by the transpose kernel through the device alias of the host arrays when they are pinned
-    // (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory); pageable arrays keep the copy-engine path
-    void* reward_map = mapped_alias(reward_host);
+    // done: written by the transpose kernel through the device alias of the host array when it is pinned
+    // (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory); a pageable array keeps the copy-engine path.
+    // reward: identically zero for this env (6DoF.py:575), so it does not travel at all - mvrl_rov6_step_host fills the
+    // host array with zeros on the host side (once per captured pipeline) instead of shipping 4 B per environment
+    // over PCIe every step.
+    void* reward_map = nullptr;
+    reward_host = nullptr;
     uint8_t* done_map = (uint8_t*)mapped_alias(done_host);
     MVRL_CUDA(cudaEventRecord(h->ev_in, root));
     for (int i = 0; i < MvrlRov6::kStreams; ++i) MVRL_CUDA(cudaStreamWaitEvent(h->hs[i], h->ev_in, 0));
@@ -551,7 +555,9 @@ extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, 
     if (chunks < 0) chunks = -chunks;
     if (chunks > MvrlRov6::kMaxChunks) chunks = MvrlRov6::kMaxChunks;
     cudaStream_t user = (cudaStream_t)stream;
+    const bool zero_reward_now = reward_host != nullptr;   // direct mode: every call; graph mode: when the pipeline is captured
     if (!graph_mode) {
+        if (zero_reward_now) memset(reward_host, 0, (size_t)n * es);
         { const int rc = enqueue_host_step(h, n, ld, b, actions_host, obs_host, reward_host, done_host, chunks, user); if (rc != MVRL_OK) return rc; }
         MVRL_CUDA(cudaStreamSynchronize(user));
         return MVRL_OK;
@@ -571,6 +577,7 @@ extern "C" MVRL_API int mvrl_rov6_step_host(MvrlRov6* h, int64_t n, int64_t ld, 
         if (e->used < lru->used) lru = e;
     }
     if (!g) {
+        if (zero_reward_now) memset(reward_host, 0, (size_t)n * es);   // the caller's array, zero like every reward of this env
         g = lru;
         if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
         cudaGraph_t graph = nullptr;

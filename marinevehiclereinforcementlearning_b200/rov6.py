@@ -351,9 +351,11 @@ class _RovVecEnv:
         if obs_out is None:
             if getattr(self, "_h_obs", None) is None:
                 self._h_obs = torch.empty((n, self.lenObs), dtype=self.dtype).pin_memory()
-                self._h_reward = torch.empty(n, dtype=self.dtype).pin_memory()
+                self._h_reward = torch.zeros(n, dtype=self.dtype).pin_memory()   # reward == 0 (6DoF.py:575): never shipped over PCIe
                 self._h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
             obs_out, reward_out, done_out = self._h_obs, self._h_reward, self._h_done
+        elif reward_out is not None:
+            reward_out.zero_()   # caller-owned array: the library zero-fills it only when it captures the pipeline
         h = self._get_handle()
         self._bufs.action = self._action.data_ptr()
         _lib.check(h.lib.mvrl_rov6_step_host(h._h, n, self.ld, C.byref(self._bufs), C.c_void_p(actions.data_ptr()),

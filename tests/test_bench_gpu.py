@@ -28,7 +28,7 @@ def test_bench_line_contract_on_a_small_batch():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8192 * 8 * 4 and e["d2h_bytes_per_step"] == 8192 * (9 * 4 + 4 + 1)
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8192 * 8 * 4 and e["d2h_bytes_per_step"] == 8192 * (9 * 4 + 1)
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
     assert c["as_shipped_rk45_pid_port_one_core"] > 0 and c["legacy_auv_step_port_one_core"] > 0
     r5 = d["extra"]["config5_rollout"]   # config 5 rides along at every N

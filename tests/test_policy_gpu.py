@@ -1,0 +1,79 @@
+"""GPU: the fused rollout actor (csrc/mvrl_policy.cu) against a plain PyTorch fp32 restatement of the same network."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv, MlpGaussianPolicy
+
+DEV = "cuda"
+
+
+def _buffers(pol, n, seed=0):
+    ld = (n + 31) // 32 * 32
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    obs = torch.zeros((pol.obs_dim, ld), device=DEV)
+    obs[:, :n] = torch.rand((pol.obs_dim, n), generator=g, device=DEV) * 2 - 1
+    z = lambda k: torch.full((k, ld), 7.0, device=DEV)
+    return obs, z(pol.act_dim), z(pol.act_dim), z(pol.act_dim), torch.full((ld,), 7.0, device=DEV)
+
+
+@pytest.mark.parametrize("n", [1, 37, 128, 5000, 131072])
+def test_actor_matches_pytorch_reference(n):
+    pol = MlpGaussianPolicy(9, 6, device=DEV, seed=3)
+    for b in pol.biases:   # non-zero biases so that they are exercised
+        b.uniform_(-0.3, 0.3, generator=torch.Generator().manual_seed(5))
+    pol.log_std = torch.tensor([-0.5, -0.7, -0.2, -1.0, 0.1, -0.4])
+    pol.sync_weights()
+    obs, act, mean, eps, logp = _buffers(pol, n)
+    pol.act_into(obs, act, n, logp=logp, mean=mean, eps=eps, env_id0=11, step=4)
+    x = obs[:, :n].T
+    ref_bf16 = pol.reference_forward(x, round_bf16=True)       # same operand rounding as the kernel: bf16 inputs, fp32 accumulate
+    ref_fp32 = pol.reference_forward(x, round_bf16=False)      # the network in plain fp32
+    got = mean[:, :n].T
+    assert float((got - ref_bf16).abs().max()) < 6e-3          # tanh.approx (2^-11) + accumulation order
+    assert float((got - ref_fp32).abs().max()) < 4e-2          # bf16 operands: 3 significant digits
+    e = eps[:, :n].T
+    std = pol.log_std.exp().to(DEV)
+    assert torch.allclose(act[:, :n].T, (got + std * e).clamp(-1, 1), atol=1e-6)
+    assert torch.allclose(logp[:n], -0.5 * (e * e).sum(1) + pol.logp_const, atol=1e-5)
+    # nothing written beyond n (rows n .. ld keep the fill value)
+    assert bool((act[:, n:] == 7.0).all()) and bool((logp[n:] == 7.0).all())
+    if n >= 5000:   # the draws are standard normal
+        assert abs(float(e.mean())) < 0.02 and abs(float(e.std()) - 1.0) < 0.02
+        assert abs(float((e ** 3).mean())) < 0.08 and abs(float((e ** 4).mean()) - 3.0) < 0.2
+
+
+def test_actor_draws_do_not_depend_on_sharding_and_deterministic_mode():
+    pol = MlpGaussianPolicy(9, 6, device=DEV, seed=9)
+    n = 1000
+    obs, act, mean, eps, logp = _buffers(pol, n, seed=2)
+    pol.act_into(obs, act, n, eps=eps, env_id0=0, step=7)
+    lo = 512                                                    # second shard: environments 512 .. 999 with env_id0 = 512
+    obs2 = obs[:, lo:lo + 512].contiguous()                     # ld 512 (488 real environments)
+    act2, eps2 = torch.zeros_like(obs2[:6]), torch.zeros_like(obs2[:6])
+    pol.act_into(obs2, act2, n - lo, eps=eps2, env_id0=lo, step=7)
+    assert torch.equal(eps2[:, :n - lo], eps[:, lo:n]) and torch.equal(act2[:, :n - lo], act[:, lo:n])
+    pol.act_into(obs, act, n, mean=mean, step=8, deterministic=True)
+    assert torch.equal(act[:, :n], mean[:, :n])
+    a, _ = pol.predict(obs[:, :5].T.cpu().numpy(), deterministic=True)
+    assert a.shape == (5, 6) and np.allclose(a, mean[:, :5].T.cpu().numpy(), atol=1e-6)
+    a1, _ = pol.predict(np.zeros(9, dtype=np.float32), deterministic=True)
+    assert a1.shape == (6,)
+
+
+def test_rollout_step_is_actor_plus_env_step():
+    """Closed loop on the env's own buffers: actor writes env._action, the fused step reads it; 20 steps, finite, actions in range."""
+    n = 4096
+    env = BlueROV2Heavy6DoFVecEnv(n, action_mode="setpoint", dtype=torch.float32, device=DEV, maxSteps=8, auto_reset=True, seed=1)
+    pol = MlpGaussianPolicy(env.lenObs, env.lenAction, device=DEV, seed=1)
+    env.reset()
+    logp = torch.empty(env.ld, device=DEV)
+    for k in range(20):
+        pol.act(env, logp=logp)
+        obs, rew, done, _ = env.step()
+        assert float(env.actions_fm.abs().max()) <= 1.0
+    assert bool(torch.isfinite(env.systemState).all()) and bool(torch.isfinite(logp[:n]).all())
+    assert env.episode_stats()["episodes"] == 2 * n
