@@ -155,6 +155,8 @@ def load():
             "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % (LIB_PATH, CSRC_DIR))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
+        if os.environ.get("MVRL_LIB") and not hasattr(lib, name):
+            continue   # an experiment build of older sources (A/B runs); the in-tree library must export everything
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args

@@ -13,15 +13,19 @@ template <typename T> struct FlowDev {
     const T* field;
     int nt, ny, nx, nc;
     T dx, dy, dt;
+    T inv_dx, inv_dy, inv_dt;   // host-computed reciprocals (step kernel: three multiplies instead of three IEEE divisions)
 };
 
 // flowGenerator.py:97-136: trilinear interpolation, indices clamped to the grid,
 // weights NOT clamped (extrapolation outside, and `translate` is ignored).
 template <typename T> struct FlowCell { int kk, jj, ii; T wt, wx, wy; };
 
-template <typename T>
+// RCP = true (env step kernel): grid coordinates by multiplication with the host's reciprocals.  The result differs from
+// the quotient by at most one rounding; the interpolant is continuous across cell faces, so even a coordinate that lands on
+// the other side of a face changes the value by ~1 ulp.  The stand-alone interp entry keeps the reference's divisions.
+template <bool RCP = false, typename T>
 __device__ __forceinline__ FlowCell<T> flow_locate(const FlowDev<T>& f, T time, T x, T y) {
-    const T tt = time / f.dt, xx = x / f.dx, yy = y / f.dy;
+    const T tt = RCP ? time * f.inv_dt : time / f.dt, xx = RCP ? x * f.inv_dx : x / f.dx, yy = RCP ? y * f.inv_dy : y / f.dy;
     FlowCell<T> c;
     // clamp in floating point first: int conversion of huge / non-finite values is undefined.  fmin / fmax
     // return the non-NaN operand, so a NaN coordinate (a vehicle that diverged) indexes cell 0 and yields NaN
@@ -123,24 +127,26 @@ template <typename T> struct AuvStepArgs {
 };
 
 // dataToState: V3 of AuvEnv (verySimpleAuv.py:147-214; target at the origin, no scaling) or, for AuvEnvCyl,
-// V0 scaling against the current way-point (verySimpleAuv_cyl.py:84-115)
-template <typename T>
-__device__ __forceinline__ void observe_auv(bool cyl, T tx, T ty, T x, T y, T psi, T u, T v, T r, T heading_target, T perr_ox, T perr_oy,
+// V0 scaling against the current way-point (verySimpleAuv_cyl.py:84-115).  The scales are literals, so they are applied
+// as multiplications by their (double-rounded) reciprocals; CYL is a template parameter: the plain env has no scaling
+// at all.
+template <bool CYL, typename T>
+__device__ __forceinline__ void observe_auv(T tx, T ty, T x, T y, T psi, T u, T v, T r, T heading_target, T perr_ox, T perr_oy,
                                             T herr_o, T (&obs)[11]) {
     const T px = tx - x, py = ty - y;
     const T herr = angle_error(heading_target, psi);
-    const T pi = T(3.14159265358979323846);
-    const T sp = cyl ? T(0.2) : T(1), sdh = cyl ? T(2. / 180 * 3.14159265358979323846) : T(1), sdp = cyl ? T(0.025) : T(1);
-    const T sv = cyl ? T(0.2) : T(1), sr = cyl ? T(30. / 180. * 3.14159265358979323846) : T(1);
-    obs[0] = clampt(px / sp, T(-1), T(1));
-    obs[1] = clampt(py / sp, T(-1), T(1));
-    obs[2] = clampt(herr / (T(45. / 180.) * pi), T(-1), T(1));
-    obs[3] = clampt((herr - herr_o) / sdh, T(-1), T(1));
-    obs[4] = clampt((px - perr_ox) / sdp, T(-1), T(1));
-    obs[5] = clampt((py - perr_oy) / sdp, T(-1), T(1));
-    obs[6] = clampt(u / sv, T(-1), T(1));
-    obs[7] = clampt(v / sv, T(-1), T(1));
-    obs[8] = clampt(r / sr, T(-1), T(1));
+    constexpr double pi = 3.14159265358979323846;
+    const T isp = CYL ? T(1. / 0.2) : T(1), isdh = CYL ? T(1. / (2. / 180 * pi)) : T(1), isdp = CYL ? T(1. / 0.025) : T(1);
+    const T isv = CYL ? T(1. / 0.2) : T(1), isr = CYL ? T(1. / (30. / 180. * pi)) : T(1);
+    obs[0] = clampt(CYL ? px * isp : px, T(-1), T(1));
+    obs[1] = clampt(CYL ? py * isp : py, T(-1), T(1));
+    obs[2] = clampt(herr * T(1. / (45. / 180. * pi)), T(-1), T(1));
+    obs[3] = clampt(CYL ? (herr - herr_o) * isdh : herr - herr_o, T(-1), T(1));
+    obs[4] = clampt(CYL ? (px - perr_ox) * isdp : px - perr_ox, T(-1), T(1));
+    obs[5] = clampt(CYL ? (py - perr_oy) * isdp : py - perr_oy, T(-1), T(1));
+    obs[6] = clampt(CYL ? u * isv : u, T(-1), T(1));
+    obs[7] = clampt(CYL ? v * isv : v, T(-1), T(1));
+    obs[8] = clampt(CYL ? r * isr : r, T(-1), T(1));
     obs[9] = T(0);
     obs[10] = T(0);
 }
@@ -172,8 +178,9 @@ __device__ __forceinline__ void draw_reset_auv(const AuvDev<T>& P, unsigned long
 
 // K4: AuvEnv.step, verySimpleAuv.py:264-410
 // STAGE: the fp32 / 2-component gather goes through shared memory with cp.async (see flow_stage_issue)
-template <typename T, bool STAGE>
-__global__ void __launch_bounds__(MVRL_AUV_BLOCK)
+// fp32: 5 CTAs of 128 threads per SM (<= 102 registers); fp64 keeps what the compiler needs
+template <typename T, bool STAGE, bool CYL>
+__global__ void __launch_bounds__(MVRL_AUV_BLOCK, (sizeof(T) == 4 ? 5 : 1))
 auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     __shared__ float2 stage[STAGE ? 8 : 1][MVRL_AUV_BLOCK];
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +191,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     T heading_target = a.target[i], t_offset = a.target[ld + i];
     int iwp = 0;
     T tx = T(0), ty = T(0);   // positionTarget: the origin, or the current way-point of AuvEnvCyl
-    if (P.cyl) { iwp = a.iwp[i]; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
+    if constexpr (CYL) { iwp = a.iwp[i]; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
     const int istep = a.istep[i] + 1;
     // EVERY input is requested here, before anything waits on one of them and before the first store: the flow-cell
     // lookup below stalls on x / y / istep, and whatever is issued after it pays a second DRAM round trip; the compiler
@@ -192,20 +199,29 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     // episode, loaded at their point of use, were 25 % of the stall samples)
     T u = a.state[3 * ld + i], v = a.state[4 * ld + i], r = a.state[5 * ld + i];
     const T a0 = a.action[i], a1 = a.action[ld + i], a2 = a.action[2 * ld + i];
+    // rows of one array are ld elements apart: walk a pointer down them instead of forming base + k * ld + i (64-bit
+    // multiply-add) for each of the ~125 accesses of this kernel
+    const long row_bytes = ld * (long)sizeof(T);
     T mm[11];
+    {
+        const char* p = reinterpret_cast<const char*>(a.mults + i);
 #pragma unroll
-    for (int k = 0; k < 11; ++k) mm[k] = a.mults[k * ld + i];
+        for (int k = 0; k < 11; ++k, p += row_bytes) mm[k] = *reinterpret_cast<const T*>(p);
+    }
     const T err_o0 = a.err_o[i], err_o1 = a.err_o[ld + i], err_o2 = a.err_o[2 * ld + i];
     const T ep_return_in = a.ep_return[i];
     const uint32_t episode_in = a.auto_reset ? a.episode[i] : 0u;
     T ring[10][3];
+    {
+        const char* p = reinterpret_cast<const char*>(a.recent + i);
 #pragma unroll
-    for (int s = 0; s < 10; ++s) {
+        for (int s = 0; s < 10; ++s) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ring[s][c] = a.recent[(s * 3 + c) * ld + i];
+            for (int c = 0; c < 3; ++c, p += row_bytes) ring[s][c] = *reinterpret_cast<const T*>(p);
+        }
     }
     const T time = T(istep) * a.dt;
-    const FlowCell<T> cell = flow_locate(a.flow, time + t_offset, x, y);
+    const FlowCell<T> cell = flow_locate<true>(a.flow, time + t_offset, x, y);
     if constexpr (STAGE) flow_stage_issue(a.flow, cell, stage);   // the gather (L2) lands while the ring statistics below are set up
     bool is_done = istep >= a.max_steps;
 
@@ -236,7 +252,9 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     const T fh1 = (P.Yv * mm[6] + P.Yvv * mm[3] * tabs(vr1)) * vr1;
     const T fh2 = (P.Nr * mm[7] + P.Nrr * mm[4] * tabs(r)) * r;
     const T Fx = cs * fh0 - sn * fh1, Fy = sn * fh0 + cs * fh1;
-    const T ax = (Fx + Fx_set) / (P.m * mm[0]), ay = (Fy + Fy_set) / (P.m * mm[0]), ar = (fh2 + N_set) / (P.Izz * mm[1]);
+    // one reciprocal per inertia instead of three divisions (<= 1 ulp from the quotients)
+    const T inv_m = T(1) / (P.m * mm[0]), inv_i = T(1) / (P.Izz * mm[1]);
+    const T ax = (Fx + Fx_set) * inv_m, ay = (Fy + Fy_set) * inv_m, ar = (fh2 + N_set) * inv_i;
     // explicit Euler, position advanced with the OLD velocity (verySimpleAuv.py:321-326)
     x = x + u * a.dt;
     y = y + v * a.dt;
@@ -246,38 +264,45 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     r = r + ar * a.dt;
 
     T obs[11];
-    observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, err_o0, err_o1, err_o2, obs);
+    observe_auv<CYL>(tx, ty, x, y, psi, u, v, r, heading_target, err_o0, err_o1, err_o2, obs);
 
     T bonus = T(0);
     if (x < P.xmin || x > P.xmax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
     if (y < P.ymin || y > P.ymax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
     T perr_x = tx - x, perr_y = ty - y;
     T herr = angle_error(heading_target, psi);
-    if (P.cyl && Real<T>::sqrt(perr_x * perr_x + perr_y * perr_y) < P.wp_thr) {   // way-point reached (verySimpleAuv_cyl.py:249-253);
-        iwp = iwp + 1 < P.n_wp ? iwp + 1 : P.n_wp - 1;                            // the errors above stay relative to the OLD target
-        tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2];
+    const T perr_norm = Real<T>::sqrt(perr_x * perr_x + perr_y * perr_y);
+    if constexpr (CYL) {
+        if (perr_norm < P.wp_thr) {                              // way-point reached (verySimpleAuv_cyl.py:249-253);
+            iwp = iwp + 1 < P.n_wp ? iwp + 1 : P.n_wp - 1;      // the errors above stay relative to the OLD target
+            tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2];
+        }
     }
 
     // rmsAc: mean over components of the population std of the <= 10 recent actions (:353-355)
     T rms = T(0);
+    const T inv_cnt = T(1) / T(cnt);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         T mean = T(0);
 #pragma unroll
         for (int s = 0; s < 10; ++s) mean += (s < cnt) ? ring[s][c] : T(0);
-        mean /= T(cnt);
+        mean *= inv_cnt;
         T var = T(0);
 #pragma unroll
         for (int s = 0; s < 10; ++s) { const T d = ring[s][c] - mean; var += (s < cnt) ? d * d : T(0); }
-        rms += Real<T>::sqrt(var / T(cnt));
+        rms += Real<T>::sqrt(var * inv_cnt);
     }
-    rms /= T(3);
+    rms *= T(1. / 3.);
     const T pi = T(3.14159265358979323846);
-    const T herr_deg = tabs(herr / pi * T(180));
-    const T t0 = Real<T>::exp(T(-5) * Real<T>::sqrt(perr_x * perr_x + perr_y * perr_y));
-    const T t1 = tabs(herr) < pi / T(2) ? Real<T>::exp(T(-0.1) * herr_deg) : -Real<T>::exp(T(-0.1) * (T(180) - herr_deg));
+    const T herr_deg = tabs(herr * T(180. / 3.14159265358979323846));
+    const T t0 = Real<T>::exp(T(-5) * perr_norm);
+    // the two branches of verySimpleAuv.py:343-346 are one exponential of a selected argument with a selected sign
+    const bool facing = tabs(herr) < pi * T(0.5);
+    const T t1e = Real<T>::exp(T(-0.1) * (facing ? herr_deg : T(180) - herr_deg));
+    const T t1 = facing ? t1e : -t1e;
     const T t2 = Real<T>::exp(T(-0.6) * rms);
-    const T t3 = T(-0.1) * (a0 * a0 + a1 * a1 + a2 * a2) / T(3);
+    const T t3 = T(-0.1 / 3.) * (a0 * a0 + a1 * a1 + a2 * a2);
     const T rew = t0 + t1 + t2 + t3 + bonus;
     const T ep_ret = ep_return_in + rew;
 
@@ -307,15 +332,18 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
         ep_ret_out = T(0);
         perr_x = tx - x; perr_y = ty - y;     // (the way-point index is NOT reset: upstream sets it in __init__ only)
         herr = angle_error(heading_target, psi);
-        observe_auv(P.cyl != 0, tx, ty, x, y, psi, u, v, r, heading_target, perr_x, perr_y, herr, obs);
+        observe_auv<CYL>(tx, ty, x, y, psi, u, v, r, heading_target, perr_x, perr_y, herr, obs);
     }
     a.target[i] = heading_target;
-    if (P.cyl) a.iwp[i] = iwp;
+    if constexpr (CYL) a.iwp[i] = iwp;
     a.state[i] = x; a.state[ld + i] = y; a.state[2 * ld + i] = psi;
     a.state[3 * ld + i] = u; a.state[4 * ld + i] = v; a.state[5 * ld + i] = r;
     a.err_o[i] = perr_x; a.err_o[ld + i] = perr_y; a.err_o[2 * ld + i] = herr;
+    {
+        char* p = reinterpret_cast<char*>(a.obs + i);
 #pragma unroll
-    for (int k = 0; k < 11; ++k) a.obs[k * ld + i] = obs[k];
+        for (int k = 0; k < 11; ++k, p += row_bytes) *reinterpret_cast<T*>(p) = obs[k];
+    }
     a.reward[i] = rew;
     a.done[i] = is_done ? 1 : 0;
     a.istep[i] = istep_out;
@@ -358,7 +386,8 @@ auv_reset_kernel(const __grid_constant__ AuvResetArgs<T> a) {
     const T herr = angle_error(target, psi);
     a.err_o[i] = tx - x; a.err_o[ld + i] = ty - y; a.err_o[2 * ld + i] = herr;
     T obs[11];
-    observe_auv(a.P.cyl != 0, tx, ty, x, y, psi, T(0), T(0), T(0), target, tx - x, ty - y, herr, obs);
+    if (a.P.cyl) observe_auv<true>(tx, ty, x, y, psi, T(0), T(0), T(0), target, tx - x, ty - y, herr, obs);
+    else observe_auv<false>(tx, ty, x, y, psi, T(0), T(0), T(0), target, tx - x, ty - y, herr, obs);
 #pragma unroll
     for (int k = 0; k < 11; ++k) a.obs[k * ld + i] = obs[k];
 }

@@ -129,7 +129,6 @@ struct MvrlRov6 {
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
     bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
-    bool small_shape;  // small batches use the 64-thread / 128-register launch shape (MVRL_NO_SMALL_SHAPE=1 disables it)
     int sm_count;
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
@@ -222,7 +221,6 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->c = *cfg;
     h->sp = default_sparsity(*params);
     { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
-    { const char* e = getenv("MVRL_NO_SMALL_SHAPE"); h->small_shape = !(e && e[0] == '1'); }
     h->sm_count = 148;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) h->sm_count = v; else cudaGetLastError(); }
     to_dev(*params, h->pf);
@@ -294,13 +292,6 @@ static void launch_step(const Rov6StepArgs<T>& a, int flags, int sm_count, cudaS
     if constexpr (sizeof(T) == 4) {
         if (x2 && x2_layout_ok(a)) {
             const int64_t threads = (a.n + 1) / 2;
-            if constexpr (SP && !FAST) {
-                // small shard: every warp fits on the machine at once at 16 warps per SM (see StepLaunch<F2, 1>)
-                if ((flags & 4) == 0 && (threads + 31) / 32 <= 16 * (int64_t)sm_count) {
-                    rov6_step_kernel<F2, MODE, SP, FAST, UNROLL, 1><<<grid_for(threads, StepLaunch<F2, 1>::BLOCK), StepLaunch<F2, 1>::BLOCK, 0, s>>>(a);
-                    return;
-                }
-            }
             rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
             return;
         }
@@ -355,7 +346,7 @@ static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64
         dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, h->sm_count, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
-        const int flags = (h->x2 ? 1 : 0) | (h->small_shape ? 0 : 4);
+        const int flags = h->x2 ? 1 : 0;
         if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
         else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
     }

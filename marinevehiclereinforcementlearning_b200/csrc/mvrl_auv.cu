@@ -61,6 +61,7 @@ extern "C" MVRL_API int mvrl_auv_set_flow(MvrlAuv* h, const void* field, int nt,
 template <typename T> static FlowDev<T> flow_dev(const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt) {
     FlowDev<T> f;
     f.field = (const T*)field; f.nt = nt; f.ny = ny; f.nx = nx; f.nc = nc; f.dx = T(dx); f.dy = T(dy); f.dt = T(dt);
+    f.inv_dx = T(1. / dx); f.inv_dy = T(1. / dy); f.inv_dt = T(1. / dt);
     return f;
 }
 
@@ -91,11 +92,13 @@ template <typename T> static int auv_step_impl(const MvrlAuv* h, int64_t n, int6
     if constexpr (sizeof(T) == 4 && MVRL_AUV_STAGE_SMEM != 0) {
         // staged gather needs the interleaved (u, v) field, 8-byte aligned
         if (h->nc == 2 && (((uintptr_t)h->field) & 7u) == 0 && h->stage_smem) {
-            auv_step_kernel<T, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
+            if (a.P.cyl) auv_step_kernel<T, true, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
+            else auv_step_kernel<T, true, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
             return mvrl_check_launch("auv_step");
         }
     }
-    auv_step_kernel<T, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
+    if (a.P.cyl) auv_step_kernel<T, false, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
+    else auv_step_kernel<T, false, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
     return mvrl_check_launch("auv_step");
 }
 

@@ -203,13 +203,12 @@ __device__ MVRL_NOINLINE void rov6_auto_reset_env(const Rov6StepArgs<T>& a, long
 #ifndef MVRL_STEP_MINB_X2
 #define MVRL_STEP_MINB_X2 3   // <= 168 registers: 3 CTAs = 12 warps per SM (measured best, profiles/ r1e notes)
 #endif
-// SHAPE 0: the throughput shape.  SHAPE 1 (F2 only): the small-shard shape - 64-thread CTAs at <= 128 registers, 16 warps per
-// SM.  A 131 072-environment shard (1 Mi environments over 8 GPUs) is 2048 warps: at 168 registers only 12 x 148 = 1776 of
-// them are resident and the rest runs as a second, nearly empty wave (31.1 us per step measured where 1/8 of the 1 Mi
-// launch is 23.1 us); at 128 registers all of them are resident at once, and 2-warp CTAs spread them 14 / 13 per SM.
-template <typename V, int SHAPE = 0> struct StepLaunch { static constexpr int BLOCK = MVRL_STEP_BLOCK, MINB = (sizeof(V) == 4 ? MVRL_STEP_MINB : 1); };
-template <> struct StepLaunch<F2, 0> { static constexpr int BLOCK = MVRL_STEP_BLOCK_X2, MINB = MVRL_STEP_MINB_X2; };
-template <> struct StepLaunch<F2, 1> { static constexpr int BLOCK = 64, MINB = 8; };
+// A 64-thread / 128-register "small-shard" shape (16 warps per SM, every warp of a 131 072-environment shard resident at
+// once) was measured in round 2 and rejected: 33.4 us per step against 31.0 us with this shape - a warp needs ~18 us for one
+// env step whatever the load (8 sub-steps of ~560 dependent-ish packed instructions), so a launch this small is bound by
+// that latency and by the synchronised phases of a single wave, not by occupancy (gpurun_out/r2b).
+template <typename V> struct StepLaunch { static constexpr int BLOCK = MVRL_STEP_BLOCK, MINB = (sizeof(V) == 4 ? MVRL_STEP_MINB : 1); };
+template <> struct StepLaunch<F2> { static constexpr int BLOCK = MVRL_STEP_BLOCK_X2, MINB = MVRL_STEP_MINB_X2; };
 
 // SoA element access for one thread: environments i0 .. i0 + L - 1 of row p
 template <typename V, typename S> __device__ __forceinline__ V load_v(const S* p, long i0, bool pair) {
@@ -228,8 +227,8 @@ template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, 
     else { if (pair) *reinterpret_cast<float2*>(p + i0) = x.v; else p[i0] = x.v.x; }
 }
 
-template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL, int SHAPE = 0>
-__global__ void __launch_bounds__((StepLaunch<V, SHAPE>::BLOCK), (StepLaunch<V, SHAPE>::MINB))
+template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
+__global__ void __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
 rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     using T = typename VT<V>::S;
     constexpr int L = VT<V>::L;
@@ -262,8 +261,8 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     // Needed by the epilogue only: the way-points are copied global -> shared with cp.async (LDGSTS) now, so their
     // DRAM latency hides behind the RK4 loop without holding 6 (12) registers across it - as registers they were
     // spilled (r1i profile: STL in the prologue and LDL / long-scoreboard stalls in the epilogue).
-    __shared__ V s_path[6][StepLaunch<V, SHAPE>::BLOCK];
-    __shared__ uint32_t s_episode[StepLaunch<V, SHAPE>::BLOCK][L];   // read by the auto-reset only: one environment in max_steps
+    __shared__ V s_path[6][StepLaunch<V>::BLOCK];
+    __shared__ uint32_t s_episode[StepLaunch<V>::BLOCK][L];   // read by the auto-reset only: one environment in max_steps
     if (a.auto_reset) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_episode[threadIdx.x][0]);
         if (L == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.episode + i0));
@@ -448,28 +447,38 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     int istep[L];
     unsigned char done_flag[L];
     T ang_raw[L][3], spa[L][3];
-    // phase A - both environments of the thread in one basic block (no branch in between: the two dependency
-    // chains interleave): wrap (6DoF.py:560) and dataToState (467-483) on the fast path
+    // phase A - wrap (6DoF.py:560) and dataToState (467-483) on the fast path, for every environment of the thread at once
+    // on the value type (packed for two environments): a wrapped angle is the angle plus a whole number of turns chosen by
+    // two 0 / 1 masks, an angle error the difference plus the turns that bring it into [-pi, pi) (see angle_error_v), and
+    // all clamps are min / max pairs.  Valid while every angle is inside (-2 pi, 4 pi) and every difference inside
+    // (-2 pi, 2 pi): ONE test per environment at the end; phase B redoes the rest with the exact out-of-line functions.
+    const V tp = V(T(MVRL_TWO_PI));
+    V ang_lo = y[3], ang_hi = y[3], d_worst = V(T(0)), ang_big = V(T(0));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const V ang = y[3 + k];
+#pragma unroll
+        for (int l = 0; l < L; ++l) { ang_raw[l][k] = lane_get(ang, l); spa[l][k] = lane_get(sp[3 + k], l); }
+        ang_lo = tmin(ang_lo, ang); ang_hi = tmax(ang_hi, ang); ang_big = tmax(ang_big, tabs(ang));
+        const V wrapped = fmaf_t(tp, vmask_lt(ang, V(T(0))) - vmask_ge(ang, tp), ang);
+        const V d = sp[3 + k] - wrapped;
+        d_worst = tmax(d_worst, tabs(d));
+        const V ae = fmaf_t(tp, vmask_lt(d, V(T(-MVRL_PI))) - vmask_ge(d, V(T(MVRL_PI))), d);
+        y[3 + k] = wrapped;
+        obs_v[k] = tmax(V(T(-1)), tmin(V(T(1)), pos_v[k]));
+        obs_v[3 + k] = tmax(V(T(-1)), tmin(V(T(1)), pos_v[3 + k]));
+        obs_v[6 + k] = tmax(V(T(-1)), tmin(V(T(1)), ae * V(P.inv_ang)));
+    }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         lane_on[l] = (l == 0) || pair;
-        T ys[12], path[6], obs[9], wrapped[3];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ys[k] = lane_get(y[k], l);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) path[k] = lane_get(pos_v[k], l);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { spa[l][k] = lane_get(sp[3 + k], l); ang_raw[l][k] = ys[3 + k]; }
         istep[l] = istep_in[l] + 1;
         bool bad = lane_get(nonfinite, l) != T(0);   // NaN compares unequal
         if constexpr (sizeof(T) == 4 && !FAST) {  // outside the exact range of the fp32 sin/cos reduction
-            bad = bad || tmax(tmax(tabs(ys[3]), tabs(ys[4])), tabs(ys[5])) > T(MVRL_SINCOS_F32_MAX_ARG);
+            bad = bad || lane_get(ang_big, l) > T(MVRL_SINCOS_F32_MAX_ARG);
         }
-        ok[l] = wrap_observe6_fast(P, ys, path, spa[l], wrapped, obs) || !lane_on[l];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) lane_set(y[3 + k], l, wrapped[k]);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) lane_set(obs_v[k], l, obs[k]);
+        // all three comparisons are false for NaN: the exact path then propagates it
+        ok[l] = (lane_get(ang_lo, l) > T(-MVRL_TWO_PI) && lane_get(ang_hi, l) < T(2 * MVRL_TWO_PI) && lane_get(d_worst, l) < T(MVRL_TWO_PI)) || !lane_on[l];
         const bool is_done = istep[l] >= a.max_steps;  // 6DoF.py:569-571
         reset_lane[l] = lane_on[l] && is_done && a.auto_reset;
         n_done_t += reset_lane[l] ? 1 : 0;

@@ -57,27 +57,6 @@ def test_state_dict_round_trip_is_bitwise(kind):
         assert _nan_eq(again[key], v) if torch.is_tensor(v) else again[key] == v, (kind, key)
 
 
-def test_small_shard_launch_shape_matches_throughput_shape_bitwise(monkeypatch):
-    """fp32 batches that fit the machine at 16 warps per SM take the 64-thread / 128-register launch shape
-    (StepLaunch<F2, 1>); MVRL_NO_SMALL_SHAPE=1 forces the throughput shape.  Same arithmetic per environment: bitwise equal."""
-    n, steps = 20001, 8
-    for mode, na, sc in (("rpm", 8, 3500.0), ("setpoint", 6, 1.0), ("force", 6, 40.0)):
-        rng = np.random.default_rng(4)
-        acts = torch.as_tensor(rng.uniform(-sc, sc, (steps, n, na)), dtype=torch.float32, device=DEV)
-        kw = dict(action_mode=mode, dtype=torch.float32, device=DEV, maxSteps=3, auto_reset=True, seed=9)
-        monkeypatch.setenv("MVRL_NO_SMALL_SHAPE", "0")
-        small = BlueROV2Heavy6DoFVecEnv(n, **kw)
-        monkeypatch.setenv("MVRL_NO_SMALL_SHAPE", "1")
-        big = BlueROV2Heavy6DoFVecEnv(n, **kw)
-        assert torch.equal(small.reset(), big.reset())
-        for k in range(steps):
-            os_, _, ds, _ = small.step(acts[k])
-            ob, _, db, _ = big.step(acts[k])
-            assert torch.equal(os_, ob) and torch.equal(ds, db), (mode, k)
-            assert torch.equal(small._state, big._state) and _nan_eq(small._ctrl, big._ctrl), (mode, k)
-        assert small.episode_stats() == big.episode_stats()
-
-
 def test_calls_leave_the_callers_current_device_alone():
     """a handle's entry points run on the handle's device and restore the caller's; the stateless helpers run
     where their pointers live.  With one GPU the guard is exercised with the same ordinal; with two, across devices."""
