@@ -322,7 +322,10 @@ static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t first
     const T dtc[2] = {T(0), a.hh};
     for (int i = 0; i < 2; ++i) {
         a.pid_inv_dt[i] = T(1) / (dtc[i] > T(1e-9) ? dtc[i] : T(1e-9)); a.pid_half_dt[i] = T(0.5) * dtc[i];
-        for (int k = 0; k < 6; ++k) a.pid_kd_inv_dt[i][k] = P.pKd[k] * a.pid_inv_dt[i];
+    }
+    for (int k = 0; k < 6; ++k) {   // per-component gain block of the fp32 set-point kernels (rov6_model.cuh, pid_k)
+        const T g[8] = {P.pKp[k], P.pKd[k] * a.pid_inv_dt[0], P.pKd[k] * a.pid_inv_dt[1], P.pKi[k], P.pWind[k], P.pMax[k], T(0), T(0)};
+        for (int j = 0; j < 8; ++j) a.P.pid_k[k][j] = g[j];
     }
     a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0 + (unsigned long long)first;
