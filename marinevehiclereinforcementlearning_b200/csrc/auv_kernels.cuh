@@ -176,53 +176,75 @@ __device__ __forceinline__ void draw_reset_auv(const AuvDev<T>& P, unsigned long
     }
 }
 
-// K4: AuvEnv.step, verySimpleAuv.py:264-410
-// STAGE: the fp32 / 2-component gather goes through shared memory with cp.async (see flow_stage_issue)
-// fp32: 5 CTAs of 128 threads per SM (<= 102 registers); fp64 keeps what the compiler needs
-template <typename T, bool STAGE, bool CYL>
-__global__ void __launch_bounds__(MVRL_AUV_BLOCK, (sizeof(T) == 4 ? 5 : 1))
-auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
-    __shared__ float2 stage[STAGE ? 8 : 1][MVRL_AUV_BLOCK];
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+// Everything one environment reads, as values (loaded from global memory by the plain kernel, from the prefetched
+// shared-memory stage by the pipelined one)
+template <typename T> struct AuvIn {
+    T x, y, psi, u, v, r, a0, a1, a2, heading_target, t_offset, err_o0, err_o1, err_o2, ep_return;
+    T mm[11];
+    T ring[10][3];
+    int istep, iwp;
+    uint32_t episode;
+};
+// word index of every input inside a shared-memory stage of the pipelined kernel ([AUV_IN_WORDS][MVRL_AUV_BLOCK])
+enum { AUV_W_STATE = 0, AUV_W_ACTION = 6, AUV_W_MULTS = 9, AUV_W_TARGET = 20, AUV_W_ERR = 22, AUV_W_RET = 25, AUV_W_RING = 26,
+       AUV_W_ISTEP = 56, AUV_W_EPISODE = 57, AUV_W_IWP = 58, AUV_IN_WORDS = 59 };
+
+// the two ways the env kernel fetches its 8 flow-field corners: staged through shared memory with cp.async (fp32, 2
+// components) or straight from L2
+template <typename T> struct GatherDirect {
+    const FlowDev<T>& f;
+    __device__ __forceinline__ void issue(const FlowCell<T>&) {}
+    __device__ __forceinline__ void finish(const FlowCell<T>& c, T (&cur)[2]) {
+        const long row = (long)f.nx * f.nc, plane = (long)f.ny * row;
+        const T* p = f.field + (long)c.kk * plane + (long)c.jj * row + (long)c.ii * f.nc;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const T* q = p + k;
+            cur[k] = flow_blend(c, __ldg(q), __ldg(q + f.nc), __ldg(q + row), __ldg(q + row + f.nc),
+                                __ldg(q + plane), __ldg(q + plane + f.nc), __ldg(q + plane + row), __ldg(q + plane + row + f.nc));
+        }
+    }
+};
+// PENDING = number of cp.async groups that may stay in flight behind the gather (the pipelined kernel's prefetch of the next tile)
+template <int PENDING> struct GatherStaged {
+    const FlowDev<float>& f;
+    float2 (*slot)[MVRL_AUV_BLOCK];
+    __device__ __forceinline__ void issue(const FlowCell<float>& c) {
+        flow_stage_issue(f, c, slot);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void finish(const FlowCell<float>& c, float (&cur)[2]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");   // each thread reads back only what it copied itself: no barrier
+        flow_stage_blend(c, slot, cur);
+    }
+};
+
+// K4: AuvEnv.step, verySimpleAuv.py:264-410 - the arithmetic and the stores of ONE environment
+template <typename T, bool CYL, typename Gather, typename Prefetch>
+__device__ __forceinline__ void auv_step_env(const AuvStepArgs<T>& a, long i, const AuvIn<T>& in, Gather gather, Prefetch prefetch_next) {
     const AuvDev<T>& P = a.P;
     const long ld = a.ld;
-    T x = a.state[i], y = a.state[ld + i], psi = a.state[2 * ld + i];
-    T heading_target = a.target[i], t_offset = a.target[ld + i];
+    const long row_bytes = ld * (long)sizeof(T);
+    T x = in.x, y = in.y, psi = in.psi, u = in.u, v = in.v, r = in.r;
+    const T a0 = in.a0, a1 = in.a1, a2 = in.a2;
+    T heading_target = in.heading_target, t_offset = in.t_offset;
     int iwp = 0;
     T tx = T(0), ty = T(0);   // positionTarget: the origin, or the current way-point of AuvEnvCyl
-    if constexpr (CYL) { iwp = a.iwp[i]; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
-    const int istep = a.istep[i] + 1;
-    // EVERY input is requested here, before anything waits on one of them and before the first store: the flow-cell
-    // lookup below stalls on x / y / istep, and whatever is issued after it pays a second DRAM round trip; the compiler
-    // cannot move a load above a store through pointers it must assume to alias (profiles/ r1t: err_o, ep_return and
-    // episode, loaded at their point of use, were 25 % of the stall samples)
-    T u = a.state[3 * ld + i], v = a.state[4 * ld + i], r = a.state[5 * ld + i];
-    const T a0 = a.action[i], a1 = a.action[ld + i], a2 = a.action[2 * ld + i];
-    // rows of one array are ld elements apart: walk a pointer down them instead of forming base + k * ld + i (64-bit
-    // multiply-add) for each of the ~125 accesses of this kernel
-    const long row_bytes = ld * (long)sizeof(T);
+    if constexpr (CYL) { iwp = in.iwp; tx = P.wp[iwp][0]; ty = P.wp[iwp][1]; heading_target = P.wp[iwp][2]; }
+    const int istep = in.istep + 1;
     T mm[11];
-    {
-        const char* p = reinterpret_cast<const char*>(a.mults + i);
 #pragma unroll
-        for (int k = 0; k < 11; ++k, p += row_bytes) mm[k] = *reinterpret_cast<const T*>(p);
-    }
-    const T err_o0 = a.err_o[i], err_o1 = a.err_o[ld + i], err_o2 = a.err_o[2 * ld + i];
-    const T ep_return_in = a.ep_return[i];
-    const uint32_t episode_in = a.auto_reset ? a.episode[i] : 0u;
+    for (int k = 0; k < 11; ++k) mm[k] = in.mm[k];
     T ring[10][3];
-    {
-        const char* p = reinterpret_cast<const char*>(a.recent + i);
 #pragma unroll
-        for (int s = 0; s < 10; ++s) {
+    for (int s = 0; s < 10; ++s) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c, p += row_bytes) ring[s][c] = *reinterpret_cast<const T*>(p);
-        }
+        for (int c = 0; c < 3; ++c) ring[s][c] = in.ring[s][c];
     }
     const T time = T(istep) * a.dt;
     const FlowCell<T> cell = flow_locate<true>(a.flow, time + t_offset, x, y);
-    if constexpr (STAGE) flow_stage_issue(a.flow, cell, stage);   // the gather (L2) lands while the ring statistics below are set up
+    gather.issue(cell);      // the gather (L2) lands while the ring statistics below are set up
+    prefetch_next();         // pipelined kernel: the next tile's inputs start travelling now, behind the gather
     bool is_done = istep >= a.max_steps;
 
     // recentActions.appendleft(action): ring slot, then statistics over the valid entries
@@ -240,12 +262,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     T sn, cs;
     Real<T>::sincos(psi, &sn, &cs);
     T cur[2];
-    if constexpr (STAGE) {
-        cp_async_wait_all();   // each thread reads back only what it copied itself: no barrier needed
-        flow_stage_blend(cell, stage, cur);
-    } else {
-        flow_interp<T, 2>(a.flow, time + t_offset, x, y, cur);
-    }
+    gather.finish(cell, cur);
     const T dxv = u - cur[0], dyv = v - cur[1];
     const T vr0 = cs * dxv + sn * dyv, vr1 = -sn * dxv + cs * dyv;
     const T fh0 = (P.Xu * mm[5] + P.Xuu * mm[2] * tabs(vr0)) * vr0;
@@ -264,7 +281,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     r = r + ar * a.dt;
 
     T obs[11];
-    observe_auv<CYL>(tx, ty, x, y, psi, u, v, r, heading_target, err_o0, err_o1, err_o2, obs);
+    observe_auv<CYL>(tx, ty, x, y, psi, u, v, r, heading_target, in.err_o0, in.err_o1, in.err_o2, obs);
 
     T bonus = T(0);
     if (x < P.xmin || x > P.xmax) { if (a.stop_on_bounds) is_done = true; bonus += T(-100); }
@@ -304,7 +321,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     const T t2 = Real<T>::exp(T(-0.6) * rms);
     const T t3 = T(-0.1 / 3.) * (a0 * a0 + a1 * a1 + a2 * a2);
     const T rew = t0 + t1 + t2 + t3 + bonus;
-    const T ep_ret = ep_return_in + rew;
+    const T ep_ret = in.ep_return + rew;
 
     if (a.aux != nullptr) {  // the per-step log columns of verySimpleAuv.py:389-401 that are not state/obs
         const T vals[14] = {Fx, Fy, fh2, Fx_set, Fy_set, N_set, cur[0], cur[1], rms, t0, t1, t2, t3, bonus};
@@ -321,7 +338,7 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
 #pragma unroll
             for (int k = 0; k < 11; ++k) a.term_obs[k * ld + i] = obs[k];
         }
-        const uint32_t ep = episode_in + 1u;
+        const uint32_t ep = in.episode + 1u;
         a.episode[i] = ep;
         draw_reset_auv(P, a.seed, a.env_id0 + (unsigned long long)i, ep, a.apply_noise != 0, mm, &x, &y, &psi, &heading_target, &t_offset);
 #pragma unroll
@@ -348,6 +365,122 @@ auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
     a.done[i] = is_done ? 1 : 0;
     a.istep[i] = istep_out;
     a.ep_return[i] = ep_ret_out;
+}
+
+// Plain kernel: one environment per thread, every input requested before anything waits on one of them and before the first
+// store (the flow-cell lookup stalls on x / y / istep, and whatever is issued after it pays a second DRAM round trip; the
+// compiler cannot move a load above a store through pointers it must assume to alias - profiles/ r1t).
+// STAGE: the fp32 / 2-component gather goes through shared memory with cp.async (see flow_stage_issue).
+// fp32: 5 CTAs of 128 threads per SM (<= 102 registers); fp64 keeps what the compiler needs
+template <typename T, bool STAGE, bool CYL>
+__global__ void __launch_bounds__(MVRL_AUV_BLOCK, (sizeof(T) == 4 ? 5 : 1))
+auv_step_kernel(const __grid_constant__ AuvStepArgs<T> a) {
+    __shared__ float2 stage[STAGE ? 8 : 1][MVRL_AUV_BLOCK];
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const long ld = a.ld;
+    // rows of one array are ld elements apart: walk a pointer down them instead of forming base + k * ld + i (64-bit
+    // multiply-add) for each of the ~125 accesses of this kernel
+    const long row_bytes = ld * (long)sizeof(T);
+    AuvIn<T> in;
+    in.x = a.state[i]; in.y = a.state[ld + i]; in.psi = a.state[2 * ld + i];
+    in.heading_target = a.target[i]; in.t_offset = a.target[ld + i];
+    in.iwp = CYL ? a.iwp[i] : 0;
+    in.istep = a.istep[i];
+    in.u = a.state[3 * ld + i]; in.v = a.state[4 * ld + i]; in.r = a.state[5 * ld + i];
+    in.a0 = a.action[i]; in.a1 = a.action[ld + i]; in.a2 = a.action[2 * ld + i];
+    {
+        const char* p = reinterpret_cast<const char*>(a.mults + i);
+#pragma unroll
+        for (int k = 0; k < 11; ++k, p += row_bytes) in.mm[k] = *reinterpret_cast<const T*>(p);
+    }
+    in.err_o0 = a.err_o[i]; in.err_o1 = a.err_o[ld + i]; in.err_o2 = a.err_o[2 * ld + i];
+    in.ep_return = a.ep_return[i];
+    in.episode = a.auto_reset ? a.episode[i] : 0u;
+    {
+        const char* p = reinterpret_cast<const char*>(a.recent + i);
+#pragma unroll
+        for (int s = 0; s < 10; ++s) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c, p += row_bytes) in.ring[s][c] = *reinterpret_cast<const T*>(p);
+        }
+    }
+    auto none = [] {};
+    if constexpr (STAGE) auv_step_env<T, CYL>(a, i, in, GatherStaged<0>{a.flow, stage}, none);
+    else auv_step_env<T, CYL>(a, i, in, GatherDirect<T>{a.flow}, none);
+}
+
+// Pipelined kernel (fp32, plain AuvEnv, interleaved 2-component field): the plain kernel runs its ~3 waves in lock step -
+// every CTA of a wave loads (22 MB requested at once), then computes, then stores - so DRAM idles while the SMs compute
+// and the other way round: 0.48 of the HBM roofline (profiles/r2_c_auv_step_ncu_full_summary.txt: long_scoreboard 4.9 per
+// issue, issue slots 38 % busy).  Here a persistent CTA walks over 128-environment tiles with TWO shared-memory stages:
+// while it computes tile t out of one stage, cp.async (LDGSTS, no registers) is filling the other with the 59 input words
+// per environment of tile t + gridDim.x.  Per tile: wait for the stage -> locate the flow cell -> issue the gather ->
+// issue the prefetch of the next tile -> arithmetic (identical code: auv_step_env) -> stores.
+template <bool CYL>
+__global__ void __launch_bounds__(MVRL_AUV_BLOCK, 3)
+auv_step_pipelined_kernel(const __grid_constant__ AuvStepArgs<float> a) {
+    extern __shared__ float auv_smem[];
+    float (*in_stage)[AUV_IN_WORDS][MVRL_AUV_BLOCK] = reinterpret_cast<float (*)[AUV_IN_WORDS][MVRL_AUV_BLOCK]>(auv_smem);
+    float2 (*gather_slot)[MVRL_AUV_BLOCK] = reinterpret_cast<float2 (*)[MVRL_AUV_BLOCK]>(auv_smem + 2 * AUV_IN_WORDS * MVRL_AUV_BLOCK);
+    const int tid = threadIdx.x;
+    const long ld = a.ld, row_bytes = ld * 4;
+    const long tiles = (a.n + MVRL_AUV_BLOCK - 1) / MVRL_AUV_BLOCK;
+    auto cp4 = [](void* smem, const void* gmem) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+    };
+    // one cp.async group = the 59 input words of this thread's environment of `tile`
+    auto prefetch = [&](long tile, int stage) {
+        const long i = tile * MVRL_AUV_BLOCK + tid;
+        if (tile < tiles && i < a.n) {
+            float (*s)[MVRL_AUV_BLOCK] = in_stage[stage];
+            auto rows = [&](const void* base, int w0, int count) {
+                const char* p = reinterpret_cast<const char*>(base) + i * 4;
+#pragma unroll
+                for (int k = 0; k < count; ++k, p += row_bytes) cp4(&s[w0 + k][tid], p);
+            };
+            rows(a.state, AUV_W_STATE, 6); rows(a.action, AUV_W_ACTION, 3); rows(a.mults, AUV_W_MULTS, 11);
+            rows(a.target, AUV_W_TARGET, 2); rows(a.err_o, AUV_W_ERR, 3); rows(a.ep_return, AUV_W_RET, 1);
+            rows(a.recent, AUV_W_RING, 30); rows(a.istep, AUV_W_ISTEP, 1);
+            if (a.auto_reset) rows(a.episode, AUV_W_EPISODE, 1);
+            if constexpr (CYL) rows(a.iwp, AUV_W_IWP, 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // committed even when empty: the group count stays uniform
+    };
+    prefetch(blockIdx.x, 0);
+    int it = 0;
+    for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const long i = tile * MVRL_AUV_BLOCK + tid;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile's inputs (each thread reads only its own column: no barrier)
+        const bool live = i < a.n;
+        AuvIn<float> in;
+        const float (*s)[MVRL_AUV_BLOCK] = in_stage[stage];
+        auto w = [&](int k) { return s[k][tid]; };
+        in.x = w(0); in.y = w(1); in.psi = w(2); in.u = w(3); in.v = w(4); in.r = w(5);
+        in.a0 = w(AUV_W_ACTION); in.a1 = w(AUV_W_ACTION + 1); in.a2 = w(AUV_W_ACTION + 2);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) in.mm[k] = w(AUV_W_MULTS + k);
+        in.heading_target = w(AUV_W_TARGET); in.t_offset = w(AUV_W_TARGET + 1);
+        in.err_o0 = w(AUV_W_ERR); in.err_o1 = w(AUV_W_ERR + 1); in.err_o2 = w(AUV_W_ERR + 2);
+        in.ep_return = w(AUV_W_RET);
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) in.ring[q][c] = w(AUV_W_RING + q * 3 + c);
+        }
+        in.istep = __float_as_int(w(AUV_W_ISTEP));
+        in.episode = a.auto_reset ? (uint32_t)__float_as_int(w(AUV_W_EPISODE)) : 0u;
+        in.iwp = CYL ? __float_as_int(w(AUV_W_IWP)) : 0;
+        const long next = tile + gridDim.x;
+        auto prefetch_next = [&] { prefetch(next, stage ^ 1); };
+        if (live) {
+            auv_step_env<float, CYL>(a, i, in, GatherStaged<1>{a.flow, gather_slot}, prefetch_next);
+        } else {   // a thread beyond the batch keeps the group count in step with its warp
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            prefetch_next();
+        }
+    }
 }
 
 template <typename T> struct AuvResetArgs {
