@@ -129,7 +129,6 @@ struct MvrlRov6 {
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
     bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
-    int sm_count;
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
     // resources of mvrl_rov6_step_host (created on first use, released by destroy)
@@ -221,8 +220,6 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->c = *cfg;
     h->sp = default_sparsity(*params);
     { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
-    h->sm_count = 148;
-    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) h->sm_count = v; else cudaGetLastError(); }
     to_dev(*params, h->pf);
     to_dev(*params, h->pd);
     *out = h;
@@ -285,7 +282,7 @@ template <typename T> static bool x2_layout_ok(const Rov6StepArgs<T>& a) {
 }
 
 template <typename T, int MODE, bool SP, bool FAST>
-static void launch_step(const Rov6StepArgs<T>& a, int flags, int sm_count, cudaStream_t s) {
+static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
     const bool x2 = (flags & 1) != 0;   // two environments per thread
     // the four RK4 stages are unrolled: measured faster than the rolled loop (r1 profile notes)
     constexpr int UNROLL = MVRL_STAGE_UNROLL(T);
@@ -299,14 +296,14 @@ static void launch_step(const Rov6StepArgs<T>& a, int flags, int sm_count, cudaS
     rov6_step_kernel<T, MODE, SP, FAST, UNROLL><<<grid_for(a.n, MVRL_STEP_BLOCK), MVRL_STEP_BLOCK, 0, s>>>(a);
 }
 template <typename T, bool FAST>
-static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, int x2, int sm_count, cudaStream_t s) {
+static void dispatch_step(const Rov6StepArgs<T>& a, int mode, bool sp, int x2, cudaStream_t s) {
     switch (mode * 2 + (sp ? 1 : 0)) {
-        case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, sm_count, s); break;
-        case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, sm_count, s); break;
-        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, x2, sm_count, s); break;
-        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, x2, sm_count, s); break;
-        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, x2, sm_count, s); break;
-        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, x2, sm_count, s); break;
+        case 0: launch_step<T, ACT_RPM, false, FAST>(a, x2, s); break;
+        case 1: launch_step<T, ACT_RPM, true, FAST>(a, x2, s); break;
+        case 2: launch_step<T, ACT_FORCE, false, FAST>(a, x2, s); break;
+        case 3: launch_step<T, ACT_FORCE, true, FAST>(a, x2, s); break;
+        case 4: launch_step<T, ACT_SETPOINT, false, FAST>(a, x2, s); break;
+        default: launch_step<T, ACT_SETPOINT, true, FAST>(a, x2, s); break;
     }
 }
 
@@ -322,10 +319,7 @@ static void fill_step_args(const MvrlRov6* h, const Rov6Dev<T>& P, int64_t first
     const T dtc[2] = {T(0), a.hh};
     for (int i = 0; i < 2; ++i) {
         a.pid_inv_dt[i] = T(1) / (dtc[i] > T(1e-9) ? dtc[i] : T(1e-9)); a.pid_half_dt[i] = T(0.5) * dtc[i];
-    }
-    for (int k = 0; k < 6; ++k) {   // per-component gain block of the fp32 set-point kernels (rov6_model.cuh, pid_k)
-        const T g[8] = {P.pKp[k], P.pKd[k] * a.pid_inv_dt[0], P.pKd[k] * a.pid_inv_dt[1], P.pKi[k], P.pWind[k], P.pMax[k], T(0), T(0)};
-        for (int j = 0; j < 8; ++j) a.P.pid_k[k][j] = g[j];
+        for (int k = 0; k < 6; ++k) a.pid_kd_inv_dt[i][k] = P.pKd[k] * a.pid_inv_dt[i];
     }
     a.n_sub = h->c.n_sub; a.max_steps = h->c.max_steps;
     a.seed = h->c.seed; a.env_id0 = h->c.env_id0 + (unsigned long long)first;
@@ -346,12 +340,12 @@ static int check_step_args(const MvrlRov6* h, int64_t first, int64_t n, int64_t 
 static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64_t ld, const MvrlRov6Buffers* b, cudaStream_t s) {
     if (h->c.dtype == MVRL_F64) {
         Rov6StepArgs<double> a; fill_step_args(h, h->pd, first, n, ld, b, a);
-        dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, h->sm_count, s);
+        dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
         const int flags = h->x2 ? 1 : 0;
-        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
-        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, h->sm_count, s);
+        if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, s);
+        else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, s);
     }
 }
 

@@ -16,10 +16,7 @@ struct MvrlAuv {
     int nt, ny, nx, nc;
     double dx, dy, dtf;
     bool stage_smem;   // MVRL_AUV_NO_STAGE=1 in the environment selects the direct L2 gather instead
-    bool pipelined;    // fp32: persistent kernel with double-buffered input prefetch (MVRL_AUV_NO_PIPELINE=1 selects the plain kernel)
-    int sm_count;
 };
-static constexpr size_t kAuvPipelineSmem = (2 * AUV_IN_WORDS * MVRL_AUV_BLOCK) * sizeof(float) + 8 * MVRL_AUV_BLOCK * sizeof(float2);
 
 extern "C" MVRL_API int mvrl_auv_default_params(MvrlAuvParams* p) {
     if (!p) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_default_params: null output");
@@ -47,16 +44,6 @@ extern "C" MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* para
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
     h->p = *params; h->c = *cfg; h->field = nullptr;
     { const char* e = getenv("MVRL_AUV_NO_STAGE"); h->stage_smem = !(e && e[0] == '1'); }
-    { const char* e = getenv("MVRL_AUV_NO_PIPELINE"); h->pipelined = !(e && e[0] == '1'); }
-    h->sm_count = 148;
-    {
-        MvrlDeviceGuard guard(cfg->device);
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) h->sm_count = v;
-        cudaError_t e = cudaFuncSetAttribute(auv_step_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAuvPipelineSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(auv_step_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAuvPipelineSmem);
-        if (e != cudaSuccess) { cudaGetLastError(); h->pipelined = false; }
-    }
     *out = h;
     return MVRL_OK;
 }
@@ -105,13 +92,6 @@ template <typename T> static int auv_step_impl(const MvrlAuv* h, int64_t n, int6
     if constexpr (sizeof(T) == 4 && MVRL_AUV_STAGE_SMEM != 0) {
         // staged gather needs the interleaved (u, v) field, 8-byte aligned
         if (h->nc == 2 && (((uintptr_t)h->field) & 7u) == 0 && h->stage_smem) {
-            if (h->pipelined) {
-                const int64_t tiles = (n + MVRL_AUV_BLOCK - 1) / MVRL_AUV_BLOCK, cap = 3 * (int64_t)h->sm_count;
-                const unsigned g = (unsigned)(tiles < cap ? tiles : cap);
-                if (a.P.cyl) auv_step_pipelined_kernel<true><<<g, MVRL_AUV_BLOCK, kAuvPipelineSmem, s>>>(a);
-                else auv_step_pipelined_kernel<false><<<g, MVRL_AUV_BLOCK, kAuvPipelineSmem, s>>>(a);
-                return mvrl_check_launch("auv_step");
-            }
             if (a.P.cyl) auv_step_kernel<T, true, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
             else auv_step_kernel<T, true, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
             return mvrl_check_launch("auv_step");

@@ -15,6 +15,7 @@ template <typename T> struct Rov6StepArgs {
     T* state; const T* action; T* obs; T* reward; uint8_t* done; int32_t* istep;
     T* setpoint; T* path; T* ctrl; uint32_t* episode; T* term_obs; T* aux; double* stats;
     T pid_inv_dt[2], pid_half_dt[2];   // 1 / max(1e-9, dtc) and dtc / 2 of the PID for dtc = 0 and dtc = h/2 (host-computed, see h6)
+    T pid_kd_inv_dt[2][6];             // Kd[k] * pid_inv_dt[half]: derivative gain per unit of e - eOld (fp32 set-point kernels)
     T dt, h, hh, h6, h3;   // env step, RK4 step h = dt / n_sub and h/2, h/6, h/3 - computed on the host: kernel arguments reach the
                            // FMAs through uniform registers, whereas a value computed in the kernel occupies a vector register and
                            // makes every y + c k update an FMA with three register sources (3 instead of 2 pipe cycles as FFMA2)
@@ -336,8 +337,8 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
             if constexpr (MODE == ACT_SETPOINT) {
                 const V pose[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
                 if constexpr (DPOSE) {
-                    if (half) pid6_core_dp<true>(P, e_old, e_int, sp, pose, dpose, a.pid_half_dt[1], gcf);
-                    else pid6_core_dp<false>(P, e_old, e_int, sp, pose, dpose, a.pid_half_dt[0], gcf);
+                    if (half) pid6_core_dp<true>(P, e_old, e_int, sp, pose, dpose, a.pid_kd_inv_dt[1], a.pid_half_dt[1], gcf);
+                    else pid6_core_dp<false>(P, e_old, e_int, sp, pose, dpose, a.pid_kd_inv_dt[0], a.pid_half_dt[0], gcf);
                 } else pid6_core<false>(P, e_old, e_int, sp, pose, a.pid_inv_dt[half], a.pid_half_dt[half], gcf);
             }
             allocate_demand<V, SP>(P, g, gcf, dem);
@@ -391,7 +392,7 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
                     const auto big = vgt(zs, V(MVRL_TRIG_DELTA_MAX2));   // (NaN offsets stay on the cheap path and stay NaN)
                     if (vany(big)) {   // rare: an environment with a large offset gets the full evaluation - decided per
                                        // environment, so a result never depends on which environment shares the thread
-                        const Trig6<V> gf = trig6_out_of_line<V, FAST>(yt[3], yt[4], yt[5]);
+                        const Trig6<V> gf = trig6<V, FAST>(yt[3], yt[4], yt[5]);
                         g.sph = vsel(big, gf.sph, g.sph); g.cph = vsel(big, gf.cph, g.cph);
                         g.sth = vsel(big, gf.sth, g.sth); g.cth = vsel(big, gf.cth, g.cth);
                         g.sps = vsel(big, gf.sps, g.sps); g.cps = vsel(big, gf.cps, g.cps);

@@ -29,10 +29,6 @@ template <typename T> struct Rov6Dev {
     T rpm_max, rpm_db;
     T f_max, f_db;            // thruster force at rpm_max / at the deadband edge
     T pKp[6], pKi[6], pKd[6], pWind[6], pMax[6];
-    // the same gains once more, grouped per controlled component in the order pid6_core_dp reads them: {Kp, Kd / max(1e-9,
-    // dt) for dt = 0, the same for dt = h/2, Ki, windup, max, -, -} - two 16-byte constant loads per component instead of
-    // five 4-byte ones (the set-point loop body is limited by instruction fetch; filled by fill_step_args)
-    alignas(16) T pid_k[6][8];
     T inv_3L, act_pos, act_ang, inv_ang;  // 1/(3 Length), 2 Length, pi/4, 4/pi
     // Crb + Ca folded for the default sparsity (see body_accel): effective masses
     // m - Xudot.., m*zg, and the differences that multiply the velocity products
@@ -104,12 +100,6 @@ __device__ __forceinline__ Trig6<V> trig6(V phi, V theta, V psi) {
     sincos_t<V, FAST>(psi, &g.sps, &g.cps);
     return g;
 }
-
-// The full evaluation as an out-of-line call: the RK4 loop needs it only when an angle moved by more than 0.25 rad within
-// one stage (MVRL_TRIG_DELTA_MAX2), and ~450 inlined instructions per sub-step would otherwise sit inside the loop's
-// address range and compete with the hot path for the 32 KB instruction cache (the set-point loop is 33 KB on its own).
-template <typename V, bool FAST>
-__device__ MVRL_NOINLINE Trig6<V> trig6_out_of_line(V phi, V theta, V psi) { return trig6<V, FAST>(phi, theta, psi); }
 
 // sin / cos of (anchor + d) from the anchor's values by the addition theorem
 // with short Taylor polynomials: no range reduction, no quadrant logic, FMA pipe
@@ -458,7 +448,7 @@ __device__ __forceinline__ void pid6_core(const Rov6Dev<S>& P, V (&e_old)[6], V 
 // set-point has moved and the literal difference is the right one.
 template <bool INTEGRATE, typename V, typename S>
 __device__ __forceinline__ void pid6_core_dp(const Rov6Dev<S>& P, V (&e_old)[6], V (&e_int)[6], const V (&sp)[6],
-                                             const V (&pose)[6], const V (&dpose)[6], S half_dt, V (&out)[6]) {
+                                             const V (&pose)[6], const V (&dpose)[6], const S (&kd_inv_dt)[6], S half_dt, V (&out)[6]) {
     V e[6];
     pid6_error(sp, pose, e);
 #pragma unroll
@@ -472,11 +462,10 @@ __device__ __forceinline__ void pid6_core_dp(const Rov6Dev<S>& P, V (&e_old)[6],
         // the same t as the one before it (half_dt = 0) adds nothing to the integral - only the wind-up test applies.
         V ei = e_int[k];
         if constexpr (INTEGRATE) ei = fmaf_t(V(half_dt), e_old[k] + e[k], ei);
-        const S (&g)[8] = P.pid_k[k];
-        ei = ei * vmask_le(tabs(e[k]), V(g[4]));
-        // Kd dedt = (Kd / max(1e-9, dt)) (e - eOld): the quotient comes from the host
-        const V cvl = fmaf_t(V(g[3]), ei, fmaf_t(V(g[INTEGRATE ? 2 : 1]), de, V(g[0]) * e[k]));
-        out[k] = tmax(V(-g[5]), tmin(V(g[5]), cvl));
+        ei = ei * vmask_le(tabs(e[k]), V(P.pWind[k]));
+        // Kd dedt = (Kd / max(1e-9, dt)) (e - eOld): the quotient comes from the host (uniform register)
+        const V cvl = fmaf_t(V(P.pKi[k]), ei, fmaf_t(V(kd_inv_dt[k]), de, V(P.pKp[k]) * e[k]));
+        out[k] = tmax(V(-P.pMax[k]), tmin(V(P.pMax[k]), cvl));
         e_int[k] = ei;
         e_old[k] = e[k];
     }
