@@ -65,10 +65,19 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// GELU, tanh form (what torch._addmm_activation(use_gelu=True) / gelu(approximate="tanh") computes)
-__device__ __forceinline__ float gelu_tanh(float x) {
-    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
-    return 0.5f * x * (1.0f + tanh_fast(u));
+// GELU in its tanh form, 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) = torch gelu(approximate="tanh") - within 1e-3 of
+// the erf form that torch.nn.GELU() (the reference's activation_fn, legacy/main_00_sbl.py:100-105) evaluates, i.e. below the
+// bf16 operand rounding of this kernel
+// bias + GELU of two adjacent columns at once on the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: the
+// activation is ~55 % of this kernel's instructions when written per element), then one bf16x2 pack
+__device__ __forceinline__ unsigned gelu_pack2(float x0, float x1, float2 b) {
+    const float2 x = __fadd2_rn(make_float2(x0, x1), b);
+    const float2 x2 = __fmul2_rn(x, x);
+    const float2 u = __fmul2_rn(x, __ffma2_rn(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f)));
+    const float2 th = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    const float2 y = __ffma2_rn(h, th, h);
+    return pack_bf16(y.x, y.y);
 }
 
 // accumulators of one layer (+ bias, GELU) -> A fragments of the next: n-tiles 2kk and 2kk + 1 give k-step kk
@@ -79,10 +88,10 @@ __device__ __forceinline__ void activate_to_frags(const float (&acc)[16][4], con
         const float2 b1 = *reinterpret_cast<const float2*>(bias + 16 * kk + 8 + 2 * t);
         const float (&c0)[4] = acc[2 * kk];
         const float (&c1)[4] = acc[2 * kk + 1];
-        afr[kk][0] = pack_bf16(gelu_tanh(c0[0] + b0.x), gelu_tanh(c0[1] + b0.y));   // row g,     k = 16 kk + 2t, +1
-        afr[kk][1] = pack_bf16(gelu_tanh(c0[2] + b0.x), gelu_tanh(c0[3] + b0.y));   // row g + 8
-        afr[kk][2] = pack_bf16(gelu_tanh(c1[0] + b1.x), gelu_tanh(c1[1] + b1.y));   // row g,     k = 16 kk + 8 + 2t, +1
-        afr[kk][3] = pack_bf16(gelu_tanh(c1[2] + b1.x), gelu_tanh(c1[3] + b1.y));   // row g + 8
+        afr[kk][0] = gelu_pack2(c0[0], c0[1], b0);   // row g,     k = 16 kk + 2t, +1
+        afr[kk][1] = gelu_pack2(c0[2], c0[3], b0);   // row g + 8
+        afr[kk][2] = gelu_pack2(c1[0], c1[1], b1);   // row g,     k = 16 kk + 8 + 2t, +1
+        afr[kk][3] = gelu_pack2(c1[2], c1[3], b1);   // row g + 8
     }
 }
 
