@@ -237,7 +237,14 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     const bool pair = (L == 2) && (i0 + 1 < a.n);   // second lane holds a real environment
     const Rov6Dev<T>& P = a.P;
     const long ld = a.ld;
-    constexpr bool EXACT = (sizeof(T) == 8);
+    // fp64 used to take the literal route inside the RK4 loop as well (demand -> sqrt -> rpm -> limit -> thrust law): 8 DSQRT
+    // per stage, 22 % of the fp64 set-point kernel's instructions.  F(rpm(c)) = c is an identity up to one rounding, and the
+    // limits move to force space exactly (f_max, f_db from the host), so both precisions use it; K2 (derivs) keeps the literal
+    // chain because it reports the rpm.  MVRL_EXACT_THRUST=1 at compile time restores the literal fp64 loop.
+#ifndef MVRL_EXACT_THRUST
+#define MVRL_EXACT_THRUST 0
+#endif
+    constexpr bool EXACT = (sizeof(T) == 8) && (MVRL_EXACT_THRUST != 0);
 
     // rows of one array are ld elements apart: walk a byte pointer instead of forming base + k * ld + i0 per row.  The second
     // environment of an unpaired thread (odd batch) reads the row's padding element: rows are padded to an even ld >= n + 1.
