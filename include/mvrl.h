@@ -313,6 +313,9 @@ typedef struct MvrlAuv MvrlAuv;
 MVRL_API int mvrl_auv_default_params(MvrlAuvParams* out);
 MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* params, const MvrlAuvConfig* cfg);
 MVRL_API int mvrl_auv_destroy(MvrlAuv* h);
+/* AuvEnv.reset(applyNoise=...) is a per-call switch upstream (verySimpleAuv.py:216-229): changes whether the NEXT resets (the
+ * reset kernel and the step kernel's auto-reset) draw the coefficient / actuation multipliers; takes effect at the next launch. */
+MVRL_API int mvrl_auv_set_apply_noise(MvrlAuv* h, int apply_noise);
 /* Scaled flow field the env gathers from: device T [nt][ny][nx][nc], nc = 2 (u, v) or 3; the
  * caller keeps it alive.  dx, dy, dt are the SCALED spacings (flowGenerator.py:77-78, 94). */
 MVRL_API int mvrl_auv_set_flow(MvrlAuv* h, const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt);

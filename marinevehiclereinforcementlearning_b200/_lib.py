@@ -118,6 +118,7 @@ PROTOTYPES = {
     "mvrl_auv_default_params": (_int, [C.POINTER(MvrlAuvParams)]),
     "mvrl_auv_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlAuvParams), C.POINTER(MvrlAuvConfig)]),
     "mvrl_auv_destroy": (_int, [_vp]),
+    "mvrl_auv_set_apply_noise": (_int, [_vp, _int]),
     "mvrl_auv_set_flow": (_int, [_vp, _vp, _int, _int, _int, _int, _d, _d, _d]),
     "mvrl_auv_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp]),
     "mvrl_auv_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp, _vp, _vp]),

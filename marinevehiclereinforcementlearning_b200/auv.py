@@ -182,8 +182,8 @@ class AuvVecEnv:
         self._stats[3] = float("inf")
         self._stats[4] = float("-inf")
 
-    def _get_handle(self, apply_noise=None):
-        apply_noise = self.applyNoise if apply_noise is None else bool(apply_noise)
+    def _get_handle(self):
+        apply_noise = self.applyNoise
         f = self.flow
         key = (self.m, self.Izz, self.Xuu, self.Yvv, self.Nrr, self.Xu, self.Yv, self.Nr, self.maxForce, self.maxMoment,
                tuple(self.xMinMax), tuple(self.yMinMax), self.noiseMagCoeffs, self.noiseMagActuation, self.dt,
@@ -252,7 +252,10 @@ class AuvVecEnv:
         """verySimpleAuv.py:216-262.  ``fixedInitialValues`` = (position ``[N, 2]`` or
         ``[2]``, heading, headingTarget) as in the reference; the draws come from
         Philox keyed on (seed, global env id, episode) instead of the global numpy RNG."""
-        h = self._get_handle(apply_noise=applyNoise)
+        h = self._get_handle()
+        noise = self.applyNoise if applyNoise is None else bool(applyNoise)
+        if noise != self.applyNoise:   # a per-call switch upstream: flip it for this reset only, no new handle
+            _lib.check(h.lib.mvrl_auv_set_apply_noise(h._h, int(noise)))
         if self._needs_episode_bump:
             if mask is None:
                 self._episode += 1
@@ -271,6 +274,8 @@ class AuvVecEnv:
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
         _lib.check(h.lib.mvrl_auv_reset(h._h, self.num_envs, self.ld, C.byref(self._bufs), _lib.ptr(m), _lib.ptr(init),
                                         _lib.current_stream(self.device)))
+        if noise != self.applyNoise:   # the step kernel's auto-resets keep the constructor's setting
+            _lib.check(h.lib.mvrl_auv_set_apply_noise(h._h, int(self.applyNoise)))
         return self.state
 
     def set_actions(self, actions):

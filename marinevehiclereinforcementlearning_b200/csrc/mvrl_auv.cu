@@ -50,6 +50,12 @@ extern "C" MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* para
 
 extern "C" MVRL_API int mvrl_auv_destroy(MvrlAuv* h) { delete h; return MVRL_OK; }
 
+extern "C" MVRL_API int mvrl_auv_set_apply_noise(MvrlAuv* h, int apply_noise) {
+    if (!h) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_set_apply_noise: null handle");
+    h->c.apply_noise = apply_noise ? 1 : 0;
+    return MVRL_OK;
+}
+
 extern "C" MVRL_API int mvrl_auv_set_flow(MvrlAuv* h, const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt) {
     if (!h || !field) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_set_flow: null argument");
     if (nt < 2 || ny < 2 || nx < 2 || (nc != 2 && nc != 3)) return mvrl_fail(MVRL_EINVAL, "mvrl_auv_set_flow: need nt, ny, nx >= 2 and nc in {2, 3}");

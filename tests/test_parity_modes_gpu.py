@@ -275,3 +275,40 @@ def test_rov3_trajectory_vs_oracle(mode, dtype, steps, floors):
     print("3DoF %s %s free-running: fraction of %d envs within %.0e at steps 100 / 300 / %d: %.4f / %.4f / %.4f; median worst %.2e" %
           (mode, dtype, n, tol, steps, fracs[100], fracs[300], fracs[steps], np.median(worst)))
     assert fracs[100] >= floors[0] and fracs[300] >= floors[1] and fracs[steps] >= floors[2], (fracs, floors)
+
+
+# ----------------------------------------------------------------- generic (non-default) vehicle ------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+@pytest.mark.parametrize("mode", ["rpm", "setpoint"])
+def test_rov6_generic_vehicle_one_step_local_error(mode, dtype):
+    """The dense (non-specialised) instantiation that serves domain-randomised vehicles - off-axis CG, cross damping,
+    inertia products, net buoyancy - against the C oracle with the same parameters, step by step on all environments."""
+    from marinevehiclereinforcementlearning_b200 import Rov6Constants
+    n, steps, tol = 1024, 40, TOL[dtype]
+    p = o.Rov6Params(CG=np.array([0.01, -0.02, 0.05]), Yr=-0.3, Nv=-0.2, Kvv=-0.4, Zq=-0.1, Mw=0.2, m=11.0,
+                     I=np.array([[0.16, 0.01, -0.02], [0.01, 0.17, 0.005], [-0.02, 0.005, 0.18]]))
+    p.dispVol = 11.4 / 1000.
+    veh = Rov6Constants()
+    veh.CG, veh.Yr, veh.Nv, veh.Kvv, veh.Zq, veh.Mw, veh.m, veh.I = p.CG, p.Yr, p.Nv, p.Kvv, p.Zq, p.Mw, p.m, p.I
+    ref = c.Rov6EnvC(n, params=p, mode=MODES[mode], max_steps=10 ** 9)
+    ref.reset()
+    env = BlueROV2Heavy6DoFVecEnv(n, action_mode=mode, dtype=dtype, device=DEV, auto_reset=False, maxSteps=10 ** 9, vehicle=veh)
+    env.reset()
+    assert not env._get_handle().specialised
+    rng = np.random.default_rng(7)
+    errs, mcs, mgs, dbs = [], [], [], []
+    for k in range(steps):
+        a = torch.as_tensor(rng.uniform(-1, 1, (n, len(SCALE6[mode]))) * SCALE6[mode], dtype=dtype)
+        sync6(env, ref, mode)
+        ref.mincos[:] = 1.0
+        ref.dbmargin[:] = np.inf
+        ref.ctrl_np["margin"] = np.inf
+        env.step(a.to(DEV))
+        ref.step(a.to(torch.float64).numpy())
+        errs.append(scaled_err(env.systemState.cpu().numpy(), ref.state, slice(3, 6)))
+        mcs.append(ref.mincos.copy()); mgs.append(ref.ctrl_np["margin"].copy()); dbs.append(ref.dbmargin.copy())
+    err, mc, mg, db = map(np.concatenate, (errs, mcs, mgs, dbs))
+    well = ~((mc < 1e-2) | ((mg < 1e-7) if mode == "setpoint" else False) | ((db < 1e-4) if mode != "rpm" else False))
+    report("6DoF generic vehicle %s %s" % (mode, dtype), err, tol, well, [])
+    assert err[well].max() <= tol, err[well].max()
+    assert well.mean() >= 0.98
