@@ -142,8 +142,14 @@ MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, cons
 MVRL_API int mvrl_rov6_destroy(MvrlRov6* h);
 /* 1 if the handle runs the kernels specialised for the reference's default
  * sparsity pattern (CG on the z axis, diagonal inertia, no cross damping but
- * Mww, neutral buoyancy, default allocation pattern), 0 for the generic ones */
+ * Mww, neutral buoyancy, default allocation pattern), 0 for the generic ones;
+ * 2 if, in addition, its fp32 constants equal the compiled-in default vehicle
+ * (6DoF.py:83-218) bit for bit, so that the fp32 step kernels with literal
+ * constants are used (same results, fewer instructions) */
 MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h);
+/* The fp32 device constants a parameter set converts to, flattened (build-time helper of
+ * tools/gen_default_consts.py, which writes csrc/rov6_default_consts.h).  Returns the number of floats. */
+MVRL_API int mvrl_rov6_dev_constants_f32(const MvrlRov6Params* params, float* out, int capacity);
 
 /* One derivative evaluation per environment (debug / parity entry, K2).
  *   state  T [12][ld]; dstate T [12][ld]

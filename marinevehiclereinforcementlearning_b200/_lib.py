@@ -94,6 +94,7 @@ PROTOTYPES = {
     "mvrl_rov6_create": (_int, [C.POINTER(_vp), C.POINTER(MvrlRov6Params), C.POINTER(MvrlRov6Config)]),
     "mvrl_rov6_destroy": (_int, [_vp]),
     "mvrl_rov6_is_specialised": (_int, [_vp]),
+    "mvrl_rov6_dev_constants_f32": (_int, [C.POINTER(MvrlRov6Params), C.POINTER(C.c_float), _int]),
     "mvrl_rov6_derivs": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvrl_rov6_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp]),
     "mvrl_rov6_step_range": (_int, [_vp, _i64, _i64, _i64, C.POINTER(MvrlRov6Buffers), _vp]),
@@ -134,14 +135,48 @@ PROTOTYPES = {
 _lib = None
 
 
-def build(verbose=False):
-    """Compile libmvrl.so in-tree with nvcc for sm_100a (csrc/Makefile)."""
+def _make(verbose):
     res = subprocess.run(["make", "-j8", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("building libmvrl.so failed (see output above)")
+
+
+def default_consts_header():
+    """Text of csrc/rov6_default_consts.h for the default vehicle as THIS host computes it (numpy pinv / inv), through
+    the built library's own double -> float conversion (mvrl_rov6_dev_constants_f32); exact hex-float literals."""
+    from .rov6 import Rov6Constants
+    lib = C.CDLL(LIB_PATH)
+    lib.mvrl_rov6_dev_constants_f32.restype = _int
+    lib.mvrl_rov6_dev_constants_f32.argtypes = [C.POINTER(MvrlRov6Params), C.POINTER(C.c_float), _int]
+    params = Rov6Constants().to_struct()
+    buf = (C.c_float * 1024)()
+    n = lib.mvrl_rov6_dev_constants_f32(C.byref(params), buf, 1024)
+    if n <= 0:
+        raise RuntimeError("mvrl_rov6_dev_constants_f32 failed")
+    lits = [(float(buf[i]).hex() + "f") for i in range(n)]
+    rows = ["    " + ", ".join(lits[i:i + 6]) + "," for i in range(0, n, 6)]
+    return ("// GENERATED by marinevehiclereinforcementlearning_b200._lib.default_consts_header() (python tools/gen_default_consts.py) -\n"
+            "// do not edit.  Rov6Dev<float> of the reference's default BlueROV2 Heavy (dynamicsModel_BlueROV2_Heavy_6DoF.py:83-218,\n"
+            "// allocation by numpy pinv as resources.py:19-35), member by member in declaration order, as exact hex-float\n"
+            "// literals; the trailing 1 is thrusters_on.  The fp32 step kernels instantiated with CONSTP read these instead of\n"
+            "// the kernel argument; mvrl_rov6_create selects them only if the handle's constants match bit for bit.\n"
+            "#pragma once\n#define MVRL_ROV6_DEFAULT_WORDS %d\n#define MVRL_ROV6_DEFAULT_INIT_F32 { \\\n%s \\\n    1 }\n" % (n, " \\\n".join(rows)))
+
+
+def build(verbose=False):
+    """Compile libmvrl.so in-tree with nvcc for sm_100a (csrc/Makefile).  The default vehicle's constants are compiled
+    into the fp32 step kernels (csrc/rov6_default_consts.h, committed); if this host's numpy produces different bits
+    than the committed header holds, the header is regenerated and the library rebuilt once."""
+    _make(verbose)
+    path = os.path.join(CSRC_DIR, "rov6_default_consts.h")
+    text = default_consts_header()
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
+        _make(verbose)
     return LIB_PATH
 
 

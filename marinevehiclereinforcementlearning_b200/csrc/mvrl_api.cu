@@ -129,6 +129,7 @@ struct MvrlRov6 {
     MvrlRov6Config c;
     bool sp;  // default sparsity pattern holds -> specialised kernels
     bool x2;  // fp32: two environments per thread on the packed FFMA2 path (MVRL_NO_X2=1 in the environment disables it)
+    bool constp;  // fp32 constants equal the compiled-in default vehicle bit for bit -> kernels with literal constants (MVRL_NO_CONSTP=1 disables)
     Rov6Dev<float> pf;
     Rov6Dev<double> pd;
     // resources of mvrl_rov6_step_host (created on first use, released by destroy)
@@ -206,6 +207,21 @@ static bool default_sparsity(const MvrlRov6Params& p) {
     return true;
 }
 
+// the default vehicle as compiled into the CONSTP kernels, and the flat view both sides are compared through
+static const Rov6Dev<float> kRov6DefaultF32 = MVRL_ROV6_DEFAULT_INIT_F32;
+static constexpr size_t kRov6DevWords = offsetof(Rov6Dev<float>, thrusters_on) / sizeof(float);
+static_assert(kRov6DevWords == MVRL_ROV6_DEFAULT_WORDS, "rov6_default_consts.h is out of date: run tools/gen_default_consts.py");
+
+// Flattened fp32 device constants of a parameter set (what tools/gen_default_consts.py writes into rov6_default_consts.h)
+extern "C" MVRL_API int mvrl_rov6_dev_constants_f32(const MvrlRov6Params* params, float* out, int capacity) {
+    if (!params || !out || capacity < (int)kRov6DevWords) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_dev_constants_f32: need room for %d floats", (int)kRov6DevWords);
+    Rov6Dev<float> d;
+    memset(&d, 0, sizeof(d));
+    to_dev(*params, d);
+    memcpy(out, &d, kRov6DevWords * sizeof(float));
+    return (int)kRov6DevWords;
+}
+
 extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* params, const MvrlRov6Config* cfg) {
     if (!out || !params || !cfg) return mvrl_fail(MVRL_EINVAL, "mvrl_rov6_create: null argument");
     if (cfg->dtype != MVRL_F32 && cfg->dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "dtype must be MVRL_F32 or MVRL_F64");
@@ -220,8 +236,12 @@ extern "C" MVRL_API int mvrl_rov6_create(MvrlRov6** out, const MvrlRov6Params* p
     h->c = *cfg;
     h->sp = default_sparsity(*params);
     { const char* e = getenv("MVRL_NO_X2"); h->x2 = !(e && e[0] == '1'); }
+    memset(&h->pf, 0, sizeof(h->pf));
+    memset(&h->pd, 0, sizeof(h->pd));
     to_dev(*params, h->pf);
     to_dev(*params, h->pd);
+    { const char* e = getenv("MVRL_NO_CONSTP");
+      h->constp = !(e && e[0] == '1') && h->sp && h->pf.thrusters_on == 1 && memcmp(&h->pf, &kRov6DefaultF32, kRov6DevWords * sizeof(float)) == 0; }
     *out = h;
     return MVRL_OK;
 }
@@ -246,7 +266,7 @@ extern "C" MVRL_API int mvrl_rov6_destroy(MvrlRov6* h) {
     delete h;
     return MVRL_OK;
 }
-extern "C" MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h) { return (h && h->sp) ? 1 : 0; }
+extern "C" MVRL_API int mvrl_rov6_is_specialised(const MvrlRov6* h) { return (h && h->sp) ? (h->constp ? 2 : 1) : 0; }
 
 #define grid_for mvrl_grid_for
 #define check_launch mvrl_check_launch
@@ -289,6 +309,12 @@ static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
     if constexpr (sizeof(T) == 4) {
         if (x2 && x2_layout_ok(a)) {
             const int64_t threads = (a.n + 1) / 2;
+            if constexpr (SP && !FAST) {
+                if (flags & 8) {   // the default vehicle: constants as literals
+                    rov6_step_kernel<F2, MODE, SP, FAST, UNROLL, true><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
+                    return;
+                }
+            }
             rov6_step_kernel<F2, MODE, SP, FAST, UNROLL><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
             return;
         }
@@ -343,7 +369,7 @@ static void launch_step_range(const MvrlRov6* h, int64_t first, int64_t n, int64
         dispatch_step<double, false>(a, h->c.action_mode, h->sp, 0, s);
     } else {
         Rov6StepArgs<float> a; fill_step_args(h, h->pf, first, n, ld, b, a);
-        const int flags = h->x2 ? 1 : 0;
+        const int flags = (h->x2 ? 1 : 0) | (h->constp ? 8 : 0);
         if (h->c.fast_math) dispatch_step<float, true>(a, h->c.action_mode, h->sp, flags, s);
         else dispatch_step<float, false>(a, h->c.action_mode, h->sp, flags, s);
     }

@@ -4,6 +4,7 @@
 // one fully coalesced 128 B (fp32) / 256 B (fp64) transaction.
 #pragma once
 #include "rov6_model.cuh"
+#include "rov6_default_consts.h"   // generated: the default vehicle's constants as exact float literals (tools/gen_default_consts.py)
 
 namespace mvrl {
 
@@ -227,7 +228,13 @@ template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, 
     else { if (pair) *reinterpret_cast<float2*>(p + i0) = x.v; else p[i0] = x.v.x; }
 }
 
-template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL>
+// CONSTP (fp32, default sparsity): the vehicle constants are the COMPILE-TIME copy of the default BlueROV2 Heavy
+// (rov6_default_consts.h) instead of the kernel argument.  The ~130 distinct constants of a set-point stage do not fit the
+// 63 uniform registers, so the run-time version reloads them (173 LDCU per sub-step, 8 % of the issue slots, and the
+// loop body grows past the 32 KB instruction cache); as literals they become immediates: set-point loop 2044 -> 1818
+// instructions, force 1449 -> 1326.  The host selects this instantiation only when the handle's constants equal the
+// compiled-in ones bit for bit (mvrl_rov6_create), so the results are identical to the run-time version.
+template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL, bool CONSTP = false>
 __global__ void __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
 rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     using T = typename VT<V>::S;
@@ -235,7 +242,9 @@ rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     const long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * L;
     if (i0 >= a.n) return;
     const bool pair = (L == 2) && (i0 + 1 < a.n);   // second lane holds a real environment
-    const Rov6Dev<T>& P = a.P;
+    static_assert(!CONSTP || (sizeof(T) == 4 && SP), "compile-time constants exist for the fp32 default vehicle only");
+    constexpr Rov6Dev<float> kDefault = MVRL_ROV6_DEFAULT_INIT_F32;
+    const auto& P = [&]() -> const Rov6Dev<T>& { if constexpr (CONSTP) return kDefault; else return a.P; }();
     const long ld = a.ld;
     // fp64 used to take the literal route inside the RK4 loop as well (demand -> sqrt -> rpm -> limit -> thrust law): 8 DSQRT
     // per stage, 22 % of the fp64 set-point kernel's instructions.  F(rpm(c)) = c is an identity up to one rounding, and the

@@ -164,6 +164,11 @@ class Rov6Handle(_Handle):
     def specialised(self):
         return bool(self.lib.mvrl_rov6_is_specialised(self._h))
 
+    @property
+    def specialisation(self):
+        """0 = generic kernels, 1 = default-sparsity kernels, 2 = default vehicle: fp32 kernels with compile-time constants."""
+        return int(self.lib.mvrl_rov6_is_specialised(self._h))
+
 
 def _device_index(device):
     _lib.require_cuda()

@@ -107,3 +107,11 @@ def test_host_chunk_plan(lib):
     assert lib.mvrl_host_chunk_count(1 << 20, 4) == 4 and lib.mvrl_host_chunk_count(1 << 20, -3) == 3
     assert lib.mvrl_host_chunk_count(1000, 64) == 4          # pieces are multiples of the 256-env transpose tile
     assert lib.mvrl_host_chunk_count(1 << 20, 1000) == 64    # capped
+
+
+def test_committed_default_constants_header_is_what_this_host_generates():
+    """csrc/rov6_default_consts.h (the default vehicle's fp32 constants compiled into the CONSTP step kernels) must equal
+    what the library's own double -> float conversion gives for Rov6Constants() here; build() regenerates it otherwise."""
+    from marinevehiclereinforcementlearning_b200 import _lib
+    path = os.path.join(_lib.CSRC_DIR, "rov6_default_consts.h")
+    assert open(path).read() == _lib.default_consts_header()

@@ -57,6 +57,36 @@ def test_state_dict_round_trip_is_bitwise(kind):
         assert _nan_eq(again[key], v) if torch.is_tensor(v) else again[key] == v, (kind, key)
 
 
+def test_compile_time_constant_kernels_match_runtime_constant_kernels_bitwise(monkeypatch):
+    """The default vehicle's fp32 step kernels carry its constants as literals (CONSTP, csrc/rov6_default_consts.h) - chosen
+    only when the handle's constants equal the compiled-in ones bit for bit; MVRL_NO_CONSTP=1 keeps the kernels that read them
+    from the kernel argument.  Same values, same operations: bitwise equal, every action mode, with auto-reset."""
+    n, steps = 20001, 8
+    for mode, na, sc in (("rpm", 8, 3500.0), ("setpoint", 6, 1.0), ("force", 6, 40.0)):
+        rng = np.random.default_rng(4)
+        acts = torch.as_tensor(rng.uniform(-sc, sc, (steps, n, na)), dtype=torch.float32, device=DEV)
+        kw = dict(action_mode=mode, dtype=torch.float32, device=DEV, maxSteps=3, auto_reset=True, seed=9)
+        monkeypatch.setenv("MVRL_NO_CONSTP", "0")
+        lit = BlueROV2Heavy6DoFVecEnv(n, **kw)
+        monkeypatch.setenv("MVRL_NO_CONSTP", "1")
+        arg = BlueROV2Heavy6DoFVecEnv(n, **kw)
+        assert torch.equal(lit.reset(), arg.reset())
+        assert lit._get_handle().specialisation == 2 and arg._get_handle().specialisation == 1
+        for k in range(steps):
+            ol, _, dl, _ = lit.step(acts[k])
+            oa, _, da, _ = arg.step(acts[k])
+            assert torch.equal(ol, oa) and torch.equal(dl, da), (mode, k)
+            assert torch.equal(lit._state, arg._state) and _nan_eq(lit._ctrl, arg._ctrl), (mode, k)
+        assert lit.episode_stats() == arg.episode_stats()
+    monkeypatch.delenv("MVRL_NO_CONSTP")
+    # a vehicle that differs in one coefficient keeps the run-time constants
+    from marinevehiclereinforcementlearning_b200 import Rov6Constants
+    veh = Rov6Constants()
+    veh.Xuu = -18.0
+    other = BlueROV2Heavy6DoFVecEnv(64, action_mode="rpm", dtype=torch.float32, device=DEV, vehicle=veh)
+    assert other._get_handle().specialisation == 1
+
+
 def test_calls_leave_the_callers_current_device_alone():
     """a handle's entry points run on the handle's device and restore the caller's; the stateless helpers run
     where their pointers live.  With one GPU the guard is exercised with the same ordinal; with two, across devices."""
