@@ -309,7 +309,7 @@ static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
     if constexpr (sizeof(T) == 4) {
         if (x2 && x2_layout_ok(a)) {
             const int64_t threads = (a.n + 1) / 2;
-            if constexpr (SP && !FAST) {
+            if constexpr (SP && !FAST && MODE != ACT_RPM) {   // (rpm mode keeps its few constants in uniform registers anyway: no gain measured)
                 if (flags & 8) {   // the default vehicle: constants as literals
                     rov6_step_kernel<F2, MODE, SP, FAST, UNROLL, true><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
                     return;

@@ -26,10 +26,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULT_LIB = os.path.join(ROOT, "marinevehiclereinforcementlearning_b200", "libmvrl.so")
 
 # name -> (mangled-name regex, environments per thread)
-# the fp32 kernels the default vehicle runs are the instantiations with compile-time constants (last template argument
-# CONSTP = true); "_runtime_constants" = the same kernels reading the constants from the kernel argument
+# the fp32 force / set-point kernels the default vehicle runs are the instantiations with compile-time constants (last
+# template argument CONSTP = true); "_runtime_constants" = the same kernel reading the constants from the kernel argument
 KERNELS = {
-    "rov6_step_f32x2_rpm": (r"rov6_step_kernelINS_2F2ELi0ELb1ELb0ELi\dELb1E", 2),
+    "rov6_step_f32x2_rpm": (r"rov6_step_kernelINS_2F2ELi0ELb1ELb0ELi\dELb0E", 2),
     "rov6_step_f32x2_force": (r"rov6_step_kernelINS_2F2ELi1ELb1ELb0ELi\dELb1E", 2),
     "rov6_step_f32x2_setpoint": (r"rov6_step_kernelINS_2F2ELi2ELb1ELb0ELi\dELb1E", 2),
     "rov6_step_f32x2_setpoint_runtime_constants": (r"rov6_step_kernelINS_2F2ELi2ELb1ELb0ELi\dELb0E", 2),
