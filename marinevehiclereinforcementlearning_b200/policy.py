@@ -89,14 +89,3 @@ class MlpGaussianPolicy:
         self.act_into(o, a, n, deterministic=deterministic)
         out = a[:, :n].T.cpu().numpy()
         return (out[0] if single else out), None
-
-    def reference_forward(self, obs_nk, round_bf16=True):
-        """Plain PyTorch restatement of the network (test reference, not a product path): mean [N, act_dim].
-        ``round_bf16=True`` mirrors the kernel's arithmetic (bf16 operands, tanh-form GELU); ``False`` is the reference's
-        network as SB3 builds it: fp32 with ``torch.nn.GELU()`` (the erf form, legacy/main_00_sbl.py:100-105)."""
-        r = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if round_bf16 else (lambda t: t)
-        approx = "tanh" if round_bf16 else "none"
-        h = r(obs_nk.to(torch.float32))
-        for i in range(3):
-            h = r(torch.nn.functional.gelu(h @ r(self.weights[i].to(h.device)).T + self.biases[i].to(h.device), approximate=approx))
-        return torch.tanh(h @ r(self.weights[3].to(h.device)).T + self.biases[3].to(h.device))

@@ -11,6 +11,18 @@ if torch.cuda.is_available():
 DEV = "cuda"
 
 
+def reference_forward(pol, obs_nk, round_bf16=True):
+    """Plain PyTorch restatement of the network (the test's reference; the product has no PyTorch path): mean [N, act_dim].
+    ``round_bf16=True`` mirrors the kernel's arithmetic (bf16 operands, tanh-form GELU); ``False`` is the reference's
+    network as SB3 builds it: fp32 with ``torch.nn.GELU()`` (the erf form, legacy/main_00_sbl.py:100-105)."""
+    r = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if round_bf16 else (lambda t: t)
+    approx = "tanh" if round_bf16 else "none"
+    h = r(obs_nk.to(torch.float32))
+    for i in range(3):
+        h = r(torch.nn.functional.gelu(h @ r(pol.weights[i].to(h.device)).T + pol.biases[i].to(h.device), approximate=approx))
+    return torch.tanh(h @ r(pol.weights[3].to(h.device)).T + pol.biases[3].to(h.device))
+
+
 def _buffers(pol, n, seed=0):
     ld = (n + 31) // 32 * 32
     g = torch.Generator(device=DEV).manual_seed(seed)
@@ -30,8 +42,8 @@ def test_actor_matches_pytorch_reference(n):
     obs, act, mean, eps, logp = _buffers(pol, n)
     pol.act_into(obs, act, n, logp=logp, mean=mean, eps=eps, env_id0=11, step=4)
     x = obs[:, :n].T
-    ref_bf16 = pol.reference_forward(x, round_bf16=True)       # same operand rounding as the kernel: bf16 inputs, fp32 accumulate
-    ref_fp32 = pol.reference_forward(x, round_bf16=False)      # the reference's network: plain fp32, erf-form GELU (torch.nn.GELU())
+    ref_bf16 = reference_forward(pol, x, round_bf16=True)       # same operand rounding as the kernel: bf16 inputs, fp32 accumulate
+    ref_fp32 = reference_forward(pol, x, round_bf16=False)      # the reference's network: plain fp32, erf-form GELU (torch.nn.GELU())
     got = mean[:, :n].T
     assert float((got - ref_bf16).abs().max()) < 6e-3          # tanh.approx (2^-11) + accumulation order
     assert float((got - ref_fp32).abs().max()) < 4e-2          # bf16 operands (3 significant digits) + tanh-form GELU
