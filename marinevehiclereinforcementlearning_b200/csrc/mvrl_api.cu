@@ -290,6 +290,11 @@ int mvrl_require_device(int device) {
 #ifndef MVRL_STAGE_UNROLL_F64
 #define MVRL_STAGE_UNROLL_F64 4
 #endif
+// rpm mode with literal constants: no faster at 168 registers (its few constants sit in uniform registers anyway), but it
+// is what lets the kernel fit 128 registers without spilling (16 warps per SM)
+#ifndef MVRL_CONSTP_RPM
+#define MVRL_CONSTP_RPM 0
+#endif
 #define MVRL_STAGE_UNROLL(T) (sizeof(T) == 4 ? MVRL_STAGE_UNROLL_F32 : MVRL_STAGE_UNROLL_F64)
 
 // Two fp32 environments per thread (packed FFMA2 path) need 8-byte aligned rows.
@@ -309,7 +314,7 @@ static void launch_step(const Rov6StepArgs<T>& a, int flags, cudaStream_t s) {
     if constexpr (sizeof(T) == 4) {
         if (x2 && x2_layout_ok(a)) {
             const int64_t threads = (a.n + 1) / 2;
-            if constexpr (SP && !FAST && MODE != ACT_RPM) {   // (rpm mode keeps its few constants in uniform registers anyway: no gain measured)
+            if constexpr (SP && !FAST && (MODE != ACT_RPM || MVRL_CONSTP_RPM != 0)) {
                 if (flags & 8) {   // the default vehicle: constants as literals
                     rov6_step_kernel<F2, MODE, SP, FAST, UNROLL, true><<<grid_for(threads, StepLaunch<F2>::BLOCK), StepLaunch<F2>::BLOCK, 0, s>>>(a);
                     return;

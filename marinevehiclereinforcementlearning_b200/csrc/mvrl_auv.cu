@@ -16,7 +16,6 @@ struct MvrlAuv {
     int nt, ny, nx, nc;
     double dx, dy, dtf;
     bool stage_smem;   // MVRL_AUV_NO_STAGE=1 in the environment selects the direct L2 gather instead
-    bool x2;           // fp32 plain env: two environments per thread on the packed FP32 path (MVRL_AUV_NO_X2=1 disables it)
 };
 
 extern "C" MVRL_API int mvrl_auv_default_params(MvrlAuvParams* p) {
@@ -45,7 +44,6 @@ extern "C" MVRL_API int mvrl_auv_create(MvrlAuv** out, const MvrlAuvParams* para
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
     h->p = *params; h->c = *cfg; h->field = nullptr;
     { const char* e = getenv("MVRL_AUV_NO_STAGE"); h->stage_smem = !(e && e[0] == '1'); }
-    { const char* e = getenv("MVRL_AUV_NO_X2"); h->x2 = !(e && e[0] == '1'); }
     *out = h;
     return MVRL_OK;
 }
@@ -100,15 +98,6 @@ template <typename T> static int auv_step_impl(const MvrlAuv* h, int64_t n, int6
     if constexpr (sizeof(T) == 4 && MVRL_AUV_STAGE_SMEM != 0) {
         // staged gather needs the interleaved (u, v) field, 8-byte aligned
         if (h->nc == 2 && (((uintptr_t)h->field) & 7u) == 0 && h->stage_smem) {
-            if (h->x2 && !a.P.cyl && (ld & 1) == 0) {   // two environments per thread need 8-byte aligned rows
-                const void* ptrs[] = {a.state, a.action, a.obs, a.reward, a.istep, a.mults, a.target, a.err_o, a.recent, a.ep_return, a.episode};
-                bool ok = (((uintptr_t)a.done) & 1u) == 0;
-                for (const void* p : ptrs) ok = ok && ((((uintptr_t)p) & 7u) == 0);
-                if (ok) {
-                    auv_step_x2_kernel<<<mvrl_grid_for((n + 1) / 2, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
-                    return mvrl_check_launch("auv_step");
-                }
-            }
             if (a.P.cyl) auv_step_kernel<T, true, true><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
             else auv_step_kernel<T, true, false><<<mvrl_grid_for(n, MVRL_AUV_BLOCK), MVRL_AUV_BLOCK, 0, s>>>(a);
             return mvrl_check_launch("auv_step");

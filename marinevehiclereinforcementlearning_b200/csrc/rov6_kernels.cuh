@@ -234,8 +234,13 @@ template <typename V, typename S> __device__ __forceinline__ void store_v(S* p, 
 // loop body grows past the 32 KB instruction cache); as literals they become immediates: set-point loop 2044 -> 1818
 // instructions, force 1449 -> 1326.  The host selects this instantiation only when the handle's constants equal the
 // compiled-in ones bit for bit (mvrl_rov6_create), so the results are identical to the run-time version.
+#ifdef MVRL_STEP_MAXNREG_X2   // tuning builds: cap the registers of every kernel in this TU directly instead of through MINB
+#define MVRL_STEP_BOUNDS(V) __maxnreg__(MVRL_STEP_MAXNREG_X2)
+#else
+#define MVRL_STEP_BOUNDS(V) __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
+#endif
 template <typename V, int MODE, bool SP, bool FAST, int STAGE_UNROLL, bool CONSTP = false>
-__global__ void __launch_bounds__(StepLaunch<V>::BLOCK, StepLaunch<V>::MINB)
+__global__ void MVRL_STEP_BOUNDS(V)
 rov6_step_kernel(const __grid_constant__ Rov6StepArgs<typename VT<V>::S> a) {
     using T = typename VT<V>::S;
     constexpr int L = VT<V>::L;
