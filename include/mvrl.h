@@ -332,18 +332,26 @@ MVRL_API int mvrl_auv_reset(MvrlAuv* h, int64_t n, int64_t ld, const MvrlAuvBuff
 /* ReconstructedFlow.interp (flowGenerator.py:97-136): t T [n], xy T [2][ld] -> out T [nc][ld] */
 MVRL_API int mvrl_flow_interp(int dtype, const void* field, int nt, int ny, int nx, int nc, double dx, double dy, double dt,
                               int64_t n, int64_t ld, const void* t, const void* xy, void* out, mvrl_stream_t stream);
+/* ReconstructedFlow.__init__, the SPOD reconstruction (flowGenerator.py:15-23): baseFlowData[t] = Re(modes @ coeffs[:, t]) + lt_mean.
+ * modes fp64 [plane][n_modes] and coeffs fp64 [n_modes][nt], each complex (interleaved re, im: numpy complex128) when its
+ * *_complex flag is set, else real; mean fp64 [plane]; plane = Ny * Nx * n_fields.  out T [nt][plane] = the [Nt][Ny][Nx][3]
+ * base field; accumulation in fp64 whatever T is.  All pointers on one device. */
+MVRL_API int mvrl_flow_reconstruct(int dtype, int64_t plane, int n_modes, int nt, const double* modes, int modes_complex,
+                                   const double* coeffs, int coeffs_complex, const double* mean, void* out, mvrl_stream_t stream);
 /* ReconstructedFlow.scale on the values (flowGenerator.py:80-90): base T [cells][3] -> out T [cells][nc_out] */
 MVRL_API int mvrl_flow_scale(int dtype, int64_t cells, const void* base, void* out, int nc_out, double velocityScale,
                              double turbScale, mvrl_stream_t stream);
 
 /* CustomReplayBuffer.add (tag_00.../main_02_sbl_contrib_customBuffer.py:57-160): stores the batch of transitions and its
- * mirror images.  obs / next_obs T [11][ld], act T [3][ld], reward T [n], done [n] (SoA, as the env holds them) ->
+ * mirror images.  obs / next_obs T [11][ld], act T [3][ld], reward T [n], done [n], timeout [n] or NULL (the
+ * "TimeLimit.truncated" flags of the infos, :150-151; NULL = all false) (SoA, as the env holds them) ->
  * buf_obs / buf_next_obs T [buffer_size][n][11], buf_act T [buffer_size][n][3], buf_reward T [buffer_size][n],
- * buf_done [buffer_size][n]; transformation t (0 = identity ... 4) goes to slot (pos + t) % buffer_size, t < n_transforms. */
+ * buf_done, buf_timeout (nullable) [buffer_size][n]; transformation t (0 = identity ... 4) goes to slot
+ * (pos + t) % buffer_size, t < n_transforms.  buffer_size counts slots (SB3: transitions // n_envs). */
 MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t ld, const void* obs, const void* next_obs, const void* act,
-                                       const void* reward, const uint8_t* done, void* buf_obs, void* buf_next_obs, void* buf_act,
-                                       void* buf_reward, uint8_t* buf_done, int64_t buffer_size, int64_t pos, int n_transforms,
-                                       mvrl_stream_t stream);
+                                       const void* reward, const uint8_t* done, const uint8_t* timeout, void* buf_obs, void* buf_next_obs,
+                                       void* buf_act, void* buf_reward, uint8_t* buf_done, uint8_t* buf_timeout, int64_t buffer_size,
+                                       int64_t pos, int n_transforms, mvrl_stream_t stream);
 
 /* ------------------------------------------------------------ rollout actor -- */
 /* The policy the reference trains with SB3 (tag_00.../main_00_sbl.py:100-105: MlpPolicy, net_arch [128, 128, 128], GELU)

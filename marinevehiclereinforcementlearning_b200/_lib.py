@@ -124,7 +124,8 @@ PROTOTYPES = {
     "mvrl_auv_step": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp]),
     "mvrl_auv_reset": (_int, [_vp, _i64, _i64, C.POINTER(MvrlAuvBuffers), _vp, _vp, _vp]),
     "mvrl_flow_interp": (_int, [_int, _vp, _int, _int, _int, _int, _d, _d, _d, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "mvrl_replay_add_symmetric": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "mvrl_replay_add_symmetric": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "mvrl_flow_reconstruct": (_int, [_int, _i64, _int, _int, _vp, _int, _vp, _int, _vp, _vp, _vp]),
     "mvrl_flow_scale": (_int, [_int, _i64, _vp, _vp, _int, _d, _d, _vp]),
     "mvrl_policy_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
     "mvrl_policy_destroy": (_int, [_vp]),

@@ -480,6 +480,76 @@ __global__ void flow_scale_kernel(long cells, const T* base, T* out, int nc_out,
 }
 
 // ---------------------------------------------------------------------------
+// ReconstructedFlow.__init__ (flowGenerator.py:15-23): baseFlowData[t] = Re(modes @ coeffs[:, t]) + lt_mean, written as
+// ONE pass in the layout and precision the env reads: out T [nt][P] (P = Ny * Nx * 3 values of a plane), accumulated in
+// fp64 like the reference's numpy matmul.  modes [P][K] and coeffs [K][nt] are fp64, complex (interleaved re, im: the
+// pySPOD blobs are complex128) or real; only the real part of the product is formed (2 of the 4 real products), the mean is
+// added and the result converted in the epilogue - no [P][nt] intermediate, no transpose, no separate "+ mean" pass.
+// 64 x 64 output tile per CTA, 16 x 16 threads with a 4 x 4 micro-tile each, K in steps of 16 through shared memory.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+flow_reconstruct_kernel(long P, int K, int nt, const double* __restrict__ modes, int modes_complex, const double* __restrict__ coeffs,
+                        int coeffs_complex, const double* __restrict__ mean, T* __restrict__ out) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ double a_re[BK][BM], a_im[BK][BM], b_re[BK][BN], b_im[BK][BN];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long p0 = (long)blockIdx.x * BM;
+    const int t0 = blockIdx.y * BN;
+    const int ms = modes_complex ? 2 : 1, cs = coeffs_complex ? 2 : 1;
+    const bool imag = modes_complex && coeffs_complex;   // Re(m c) = mr cr - mi ci: the second product exists only then
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int e = threadIdx.x; e < BM * BK; e += 256) {   // modes: k contiguous
+            const int kk = e % BK, pp = e / BK;
+            const long p = p0 + pp; const int k = k0 + kk;
+            const bool in = p < P && k < K;
+            const double* q = modes + (p * K + k) * ms;
+            a_re[kk][pp] = in ? q[0] : 0.;
+            a_im[kk][pp] = (in && imag) ? q[1] : 0.;
+        }
+#pragma unroll
+        for (int e = threadIdx.x; e < BN * BK; e += 256) {   // coeffs: t contiguous
+            const int tt = e % BN, kk = e / BN;
+            const int t = t0 + tt, k = k0 + kk;
+            const bool in = t < nt && k < K;
+            const double* q = coeffs + ((long)k * nt + t) * cs;
+            b_re[kk][tt] = in ? q[0] : 0.;
+            b_im[kk][tt] = (in && imag) ? q[1] : 0.;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double ar[4], ai[4], br[4], bi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ar[i] = a_re[kk][tx + 16 * i]; ai[i] = a_im[kk][tx + 16 * i]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { br[j] = b_re[kk][ty + 16 * j]; bi[j] = b_im[kk][ty + 16 * j]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(-ai[i], bi[j], fma(ar[i], br[j], acc[i][j]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = t0 + ty + 16 * j;
+        if (t >= nt) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long p = p0 + tx + 16 * i;
+            if (p < P) out[(long)t * P + p] = T(acc[i][j] + mean[p]);   // consecutive threads -> consecutive p: coalesced rows
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // CustomReplayBuffer.add (tag_00.../main_02_sbl_contrib_customBuffer.py:57-160): every transition of the
 // legacy env is stored together with its mirror images (obs / action sign flips); reward and done are
 // unchanged.  Slot (pos + t) % buffer_size holds transformation t of the whole batch, as upstream.
@@ -493,8 +563,8 @@ __constant__ float kReplaySignAct[5][3] = {{1, 1, 1}, {-1, -1, 1}, {-1, 1, 1}, {
 
 template <typename T>
 __global__ void replay_add_symmetric_kernel(long n, long ld, const T* obs, const T* next_obs, const T* act, const T* reward,
-                                            const uint8_t* done, T* b_obs, T* b_next, T* b_act, T* b_rew, uint8_t* b_done,
-                                            long buffer_size, long pos, int n_transforms) {
+                                            const uint8_t* done, const uint8_t* timeout, T* b_obs, T* b_next, T* b_act, T* b_rew,
+                                            uint8_t* b_done, uint8_t* b_timeout, long buffer_size, long pos, int n_transforms) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n * n_transforms) return;
     const int t = (int)(e / n);
@@ -510,6 +580,7 @@ __global__ void replay_add_symmetric_kernel(long n, long ld, const T* obs, const
     for (int k = 0; k < 3; ++k) b_act[row * 3 + k] = act[k * ld + i] * T(kReplaySignAct[t][k]);
     b_rew[row] = reward[i];
     b_done[row] = done[i];
+    if (b_timeout != nullptr) b_timeout[row] = timeout != nullptr ? timeout[i] : 0;   // main_02...:150-151
 }
 
 }  // namespace mvrl

@@ -171,10 +171,25 @@ extern "C" MVRL_API int mvrl_flow_scale(int dtype, int64_t cells, const void* ba
     return mvrl_check_launch("flow_scale");
 }
 
+extern "C" MVRL_API int mvrl_flow_reconstruct(int dtype, int64_t plane, int n_modes, int nt, const double* modes, int modes_complex,
+                                              const double* coeffs, int coeffs_complex, const double* mean, void* out, mvrl_stream_t stream) {
+    if (!modes || !coeffs || !mean || !out) return mvrl_fail(MVRL_EINVAL, "mvrl_flow_reconstruct: null argument");
+    if (plane < 1 || n_modes < 1 || nt < 1) return mvrl_fail(MVRL_EINVAL, "mvrl_flow_reconstruct: plane, n_modes and nt must be >= 1");
+    if (dtype != MVRL_F32 && dtype != MVRL_F64) return mvrl_fail(MVRL_EINVAL, "bad dtype");
+    MVRL_ON_DEVICE_OF(out, modes, "mvrl_flow_reconstruct");
+    if (mvrl_device_of(coeffs) != mvrl_dev_out_ || mvrl_device_of(mean) != mvrl_dev_out_)
+        return mvrl_fail(MVRL_EINVAL, "mvrl_flow_reconstruct: coeffs / mean are not on the output's device");
+    const dim3 grid((unsigned)((plane + 63) / 64), (unsigned)((nt + 63) / 64));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MVRL_F64) flow_reconstruct_kernel<double><<<grid, 256, 0, s>>>(plane, n_modes, nt, modes, modes_complex, coeffs, coeffs_complex, mean, (double*)out);
+    else flow_reconstruct_kernel<float><<<grid, 256, 0, s>>>(plane, n_modes, nt, modes, modes_complex, coeffs, coeffs_complex, mean, (float*)out);
+    return mvrl_check_launch("flow_reconstruct");
+}
+
 extern "C" MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t ld, const void* obs, const void* next_obs, const void* act,
-                                                  const void* reward, const uint8_t* done, void* buf_obs, void* buf_next_obs, void* buf_act,
-                                                  void* buf_reward, uint8_t* buf_done, int64_t buffer_size, int64_t pos, int n_transforms,
-                                                  mvrl_stream_t stream) {
+                                                  const void* reward, const uint8_t* done, const uint8_t* timeout, void* buf_obs, void* buf_next_obs,
+                                                  void* buf_act, void* buf_reward, uint8_t* buf_done, uint8_t* buf_timeout, int64_t buffer_size,
+                                                  int64_t pos, int n_transforms, mvrl_stream_t stream) {
     if (!obs || !next_obs || !act || !reward || !done || !buf_obs || !buf_next_obs || !buf_act || !buf_reward || !buf_done)
         return mvrl_fail(MVRL_EINVAL, "mvrl_replay_add_symmetric: null argument");
     if (n < 0 || ld < n || buffer_size < 1 || pos < 0 || pos >= buffer_size || n_transforms < 1 || n_transforms > 5 || n_transforms > buffer_size)
@@ -185,12 +200,12 @@ extern "C" MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t 
     const unsigned g = mvrl_grid_for(n * n_transforms, 256);
     if (dtype == MVRL_F64)
         replay_add_symmetric_kernel<double><<<g, 256, 0, s>>>(n, ld, (const double*)obs, (const double*)next_obs, (const double*)act, (const double*)reward,
-                                                              done, (double*)buf_obs, (double*)buf_next_obs, (double*)buf_act, (double*)buf_reward, buf_done,
-                                                              buffer_size, pos, n_transforms);
+                                                              done, timeout, (double*)buf_obs, (double*)buf_next_obs, (double*)buf_act, (double*)buf_reward,
+                                                              buf_done, buf_timeout, buffer_size, pos, n_transforms);
     else if (dtype == MVRL_F32)
         replay_add_symmetric_kernel<float><<<g, 256, 0, s>>>(n, ld, (const float*)obs, (const float*)next_obs, (const float*)act, (const float*)reward,
-                                                             done, (float*)buf_obs, (float*)buf_next_obs, (float*)buf_act, (float*)buf_reward, buf_done,
-                                                             buffer_size, pos, n_transforms);
+                                                             done, timeout, (float*)buf_obs, (float*)buf_next_obs, (float*)buf_act, (float*)buf_reward,
+                                                             buf_done, buf_timeout, buffer_size, pos, n_transforms);
     else return mvrl_fail(MVRL_EINVAL, "bad dtype");
     return mvrl_check_launch("replay_add_symmetric");
 }

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import torch
 
-from ..auv import FlowField
+from .. import _lib
+from ..auv import FlowField, _device_index
 
 
 def synthetic_base_field(lt_mean, nt, seed=7, sigma=0.05, kind="noise"):
@@ -47,19 +48,43 @@ class ReconstructedFlow(FlowField):
         coeffs = np.load(os.path.join(dataDir, "coeffs.npy"))
         modes = np.load(os.path.join(dataDir, "modes_r.npy"))
         self.lt_mean = np.load(os.path.join(dataDir, "ltm.npy"))
-        # flowGenerator.py:20-23: baseFlowData[t] = Re(modes @ coeffs[:, t]) + mean - one GEMM
-        # [Ny*Nx*3, nModes] x [nModes, Nt] on the device instead of a Python loop over time levels
-        dev = torch.device(device)
-        m = torch.as_tensor(modes, device=dev)
-        c = torch.as_tensor(coeffs, device=dev).to(m.dtype)
-        rec = torch.matmul(m.reshape(-1, m.shape[-1]), c)
-        rec = (rec.real if rec.is_complex() else rec).T.reshape((c.shape[1],) + tuple(m.shape[:-1]))
-        base = rec.to(torch.float64) + torch.as_tensor(self.lt_mean, device=dev)
+        base = self.reconstruct(modes, coeffs, self.lt_mean, dtype=dtype, device=device)
         with open(os.path.join(dataDir, "params_coeffs.yaml"), "r") as infile:
             params = yaml.safe_load(infile)
         coords = np.load(os.path.join(dataDir, "turbulence_coords.npy"))
         dx, dy = self._check_spacing(coords)
         super().__init__(base, baseDx=dx, baseDy=dy, baseDt=params["time_step"], baseCoords=coords, dtype=dtype, device=device)
+
+    @staticmethod
+    def reconstruct(modes, coeffs, lt_mean, dtype=torch.float32, device="cuda"):
+        """flowGenerator.py:20-23: ``baseFlowData[t] = Re(modes @ coeffs[:, t]) + lt_mean`` for every time level at once, by
+        kernel ``mvrl_flow_reconstruct`` (fp64 accumulation, real part / mean / conversion to ``dtype`` fused into the
+        epilogue, output already in the ``[Nt, Ny, Nx, 3]`` layout).  ``modes [Ny, Nx, 3, K]`` and ``coeffs [K, Nt]`` real or
+        complex (the pySPOD blobs are complex128)."""
+        lib = _lib.load()
+        dev = torch.device("cuda", _device_index(device))
+        modes, coeffs = np.asarray(modes), np.asarray(coeffs)
+        if modes.ndim < 2 or coeffs.ndim != 2 or modes.shape[-1] != coeffs.shape[0]:
+            raise ValueError("modes [..., K] and coeffs [K, Nt] do not match: %s, %s" % (modes.shape, coeffs.shape))
+        if tuple(np.shape(lt_mean)) != tuple(modes.shape[:-1]):
+            raise ValueError("lt_mean %s does not match the modes' plane %s" % (np.shape(lt_mean), modes.shape[:-1]))
+        k, nt = coeffs.shape
+        plane = int(np.prod(modes.shape[:-1]))
+
+        def as_f64(a):   # complex128 -> interleaved (re, im) doubles, anything real -> float64
+            cplx = np.iscomplexobj(a)
+            a = np.ascontiguousarray(a, dtype=np.complex128 if cplx else np.float64)
+            return torch.as_tensor(a.view(np.float64), device=dev), int(cplx)
+
+        m, m_c = as_f64(modes.reshape(plane, k))
+        c, c_c = as_f64(coeffs)
+        mean = torch.as_tensor(np.ascontiguousarray(lt_mean, dtype=np.float64).reshape(-1), device=dev)
+        out = torch.empty((nt,) + tuple(modes.shape[:-1]), dtype=dtype, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvrl_flow_reconstruct(_lib.torch_dtype_code(dtype), plane, k, nt, _lib.ptr(m), m_c, _lib.ptr(c), c_c,
+                                                 _lib.ptr(mean), _lib.ptr(out), _lib.current_stream(dev)))
+            torch.cuda.current_stream(dev).synchronize()   # m, c, mean die with this frame
+        return out
 
     @staticmethod
     def _check_spacing(coords):

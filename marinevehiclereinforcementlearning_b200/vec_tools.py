@@ -267,21 +267,30 @@ class SymmetryReplayBuffer:
     """``CustomReplayBuffer`` of tag_00.../main_02_sbl_contrib_customBuffer.py:57-160 on the device: every
     ``add`` stores the batch of transitions of the legacy env plus its four mirror images in consecutive
     slots, until the buffer has rolled over more than twice; then only the real transitions.  ``add`` takes
-    the env's feature-major buffers directly (no transposes, no host copy)."""
+    the env's feature-major buffers directly (no transposes, no host copy).
+
+    ``buffer_size`` counts TRANSITIONS like upstream: SB3's ``ReplayBuffer.__init__`` (the base class the reference
+    subclasses) keeps ``max(buffer_size // n_envs, 1)`` slots of ``n_envs`` transitions each, and so does this class
+    (attribute ``buffer_size`` = slots afterwards, as in SB3).  ``timeouts`` holds the ``TimeLimit.truncated`` flags
+    (``handle_timeout_termination=True`` is hard-wired upstream, :72-73)."""
     N_TRANSFORMS = 5
 
     def __init__(self, buffer_size, n_envs, dtype=torch.float32, device="cuda", ld=None):
-        self.buffer_size, self.n_envs = int(buffer_size), int(n_envs)
+        self.n_envs = int(n_envs)
+        self.buffer_size = max(int(buffer_size) // self.n_envs, 1)
         self.dtype, self.device = dtype, torch.device(device)
         self.ld = int(ld) if ld is not None else self.n_envs
         z = lambda *shape, dt=dtype: torch.zeros(shape, dtype=dt, device=self.device)
         self.observations, self.next_observations = z(self.buffer_size, self.n_envs, 11), z(self.buffer_size, self.n_envs, 11)
         self.actions, self.rewards = z(self.buffer_size, self.n_envs, 3), z(self.buffer_size, self.n_envs)
         self.dones = z(self.buffer_size, self.n_envs, dt=torch.uint8)
+        self.timeouts = z(self.buffer_size, self.n_envs, dt=torch.uint8)
         self.pos, self.full, self.nRollovers = 0, False, 0
 
-    def add(self, obs_fm, next_obs_fm, action_fm, reward, done):
-        """obs_fm / next_obs_fm ``[11, ld]``, action_fm ``[3, ld]``, reward ``[>= n]``, done uint8 ``[>= n]``."""
+    def add(self, obs_fm, next_obs_fm, action_fm, reward, done, timeouts=None):
+        """obs_fm / next_obs_fm ``[11, ld]``, action_fm ``[3, ld]``, reward ``[>= n]``, done uint8 ``[>= n]``;
+        ``timeouts`` (optional, uint8 / bool ``[>= n]``, or the list of ``infos`` dicts of a ``VecEnv.step``): the
+        ``TimeLimit.truncated`` flags, all false when omitted."""
         lib = _lib.load()
         # position bookkeeping exactly as upstream (:139-160): the roll-over test sits inside the loop over the
         # transformations, so the mirror images stop in the middle of an add() when the third roll-over happens
@@ -295,10 +304,16 @@ class SymmetryReplayBuffer:
                 self.full, self.pos = True, 0
                 self.nRollovers += 1
         done = done if done.dtype == torch.uint8 else done.to(torch.uint8)
+        if timeouts is not None:
+            if isinstance(timeouts, (list, tuple)):   # infos, as upstream's add() receives them (:150-151)
+                timeouts = np.array([bool(i.get("TimeLimit.truncated", False)) for i in timeouts], dtype=np.uint8)
+            timeouts = torch.as_tensor(timeouts, device=self.device)
+            timeouts = timeouts if timeouts.dtype == torch.uint8 else timeouts.to(torch.uint8)
         _lib.check(lib.mvrl_replay_add_symmetric(
             _lib.torch_dtype_code(self.dtype), self.n_envs, obs_fm.stride(0), _lib.ptr(obs_fm), _lib.ptr(next_obs_fm), _lib.ptr(action_fm),
-            _lib.ptr(reward), _lib.ptr(done), _lib.ptr(self.observations), _lib.ptr(self.next_observations), _lib.ptr(self.actions),
-            _lib.ptr(self.rewards), _lib.ptr(self.dones), self.buffer_size, pos0, nt, _lib.current_stream(self.device)))
+            _lib.ptr(reward), _lib.ptr(done), _lib.ptr(timeouts), _lib.ptr(self.observations), _lib.ptr(self.next_observations),
+            _lib.ptr(self.actions), _lib.ptr(self.rewards), _lib.ptr(self.dones), _lib.ptr(self.timeouts), self.buffer_size, pos0, nt,
+            _lib.current_stream(self.device)))
 
     def size(self):
         return self.buffer_size if self.full else self.pos
@@ -308,4 +323,5 @@ class SymmetryReplayBuffer:
         slot = torch.randint(0, self.size(), (batch_size,), device=self.device, generator=generator)
         env = torch.randint(0, self.n_envs, (batch_size,), device=self.device, generator=generator)
         return {"observations": self.observations[slot, env], "next_observations": self.next_observations[slot, env],
-                "actions": self.actions[slot, env], "rewards": self.rewards[slot, env], "dones": self.dones[slot, env]}
+                "actions": self.actions[slot, env], "rewards": self.rewards[slot, env], "dones": self.dones[slot, env],
+                "timeouts": self.timeouts[slot, env]}

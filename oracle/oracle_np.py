@@ -806,6 +806,24 @@ class FlowOracle:
         self.baseDx, self.baseDy, self.baseDt = float(base_dx), float(base_dy), float(base_dt)
         self.scale(1., 1., 1.)
 
+    @staticmethod
+    def reconstruct(modes, coeffs, lt_mean):
+        """legacy/flowGenerator.py:20-23: ``baseFlowData[t] = Re(modes @ coeffs[:, t]) + lt_mean``, one time level after
+        the other like the reference.  modes [Ny, Nx, 3, K], coeffs [K, Nt] (complex or real) -> [Nt, Ny, Nx, 3]."""
+        modes, coeffs = np.asarray(modes), np.asarray(coeffs)
+        base = np.zeros((coeffs.shape[1],) + modes.shape[:-1])
+        for it in range(base.shape[0]):
+            base[it] = np.real(np.matmul(modes, coeffs[:, it])) + lt_mean
+        return base
+
+    def intensity(self):
+        """legacy/flowGenerator.py:47-51 (evaluated on ``flowData`` after ``scale(1, 1, 1)``): uPrime, vPrime, TI, baseTI."""
+        f = self.baseFlowData
+        up = np.sqrt(np.sum((f[:, :, :, 0] - 1.) ** 2., axis=0) / f.shape[0])
+        vp = np.sqrt(np.sum((f[:, :, :, 1] - 0.) ** 2., axis=0) / f.shape[0])
+        ti = np.sqrt(0.5 * (up + vp))
+        return up, vp, ti, ti[ti.shape[0] // 2, ti.shape[1] // 2]
+
     def scale(self, sizeScale, velocityScale, turbScale, translate=(0, 0)):
         """legacy/flowGenerator.py:53-95.  ``translate`` only moves the plotting
         coordinates; ``interp`` ignores it (bug-compatible)."""
@@ -1078,3 +1096,39 @@ class AuvCylEnvOracle(AuvEnvOracle):
         self.i_wp = np.where(reached, np.minimum(self.waypoints.shape[0] - 1, self.i_wp + 1), self.i_wp)
         self.heading_target = self.waypoints[self.i_wp, 2].copy()
         return perr, herr
+
+
+# ==========================================================================
+# legacy: CustomReplayBuffer.add (legacy/main_02_sbl_contrib_customBuffer.py:57-160)
+# ==========================================================================
+class ReplayBufferOracle:
+    """The symmetry-augmenting replay buffer.  Storage as set up by stable_baselines3's ``ReplayBuffer.__init__`` (the
+    base class, not in the reference checkout; 2.x ``common/buffers.py``): ``max(buffer_size // n_envs, 1)`` slots of
+    ``n_envs`` transitions.  ``add`` follows main_02...:75-160 line by line."""
+    T_OBS = np.array([[1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], [-1, -1, 1, 1, -1, -1, -1, -1, 1, 1, 1], [-1, 1, 1, 1, -1, 1, -1, 1, 1, 1, 1],
+                      [1, -1, 1, 1, 1, -1, 1, -1, 1, 1, 1], [1, 1, -1, 1, 1, 1, 1, 1, -1, 1, 1]], dtype=float)   # :107-118
+    T_ACT = np.array([[1, 1, 1], [-1, -1, 1], [-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=float)                    # :119-125
+
+    def __init__(self, buffer_size, n_envs, dtype=np.float32):
+        self.n_envs = int(n_envs)
+        self.buffer_size = max(int(buffer_size) // self.n_envs, 1)
+        z = lambda *shape: np.zeros(shape, dtype=dtype)
+        self.observations, self.next_observations = z(self.buffer_size, n_envs, 11), z(self.buffer_size, n_envs, 11)
+        self.actions, self.rewards = z(self.buffer_size, n_envs, 3), z(self.buffer_size, n_envs)
+        self.dones, self.timeouts = z(self.buffer_size, n_envs), z(self.buffer_size, n_envs)
+        self.pos, self.full, self.nRollovers = 0, False, 0
+
+    def add(self, obs, next_obs, action, reward, done, timeouts=None):
+        for i in range(5):
+            if self.nRollovers > 2 and i != 0:      # :143-145: no mirror images after the third roll-over
+                continue
+            p = self.pos
+            self.observations[p] = np.asarray(obs) * self.T_OBS[i]
+            self.next_observations[p] = np.asarray(next_obs) * self.T_OBS[i]
+            self.actions[p] = np.asarray(action) * self.T_ACT[i]
+            self.rewards[p], self.dones[p] = reward, done
+            self.timeouts[p] = 0 if timeouts is None else timeouts
+            self.pos += 1
+            if self.pos == self.buffer_size:        # :155-158
+                self.full, self.pos = True, 0
+                self.nRollovers += 1

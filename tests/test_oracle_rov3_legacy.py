@@ -99,6 +99,40 @@ def test_flow_scale_and_interp():
     assert flow.time[flow.time.shape[0] // 4] == float(g["flow_time_quarter"])
 
 
+def test_spod_reconstruction_oracle_vs_reference_constructor():
+    """oracle.FlowOracle.reconstruct / intensity against the golden file written by the UNMODIFIED
+    ReconstructedFlow.__init__ (flowGenerator.py:14-51) on synthetic blobs (tests/golden/gen_golden_spod.py)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from _spod_blobs import spod_blobs
+    g = load_golden("spod")
+    for tag, cplx in (("c", True), ("r", False)):
+        modes, coeffs = spod_blobs(g["ltm"].shape, int(g["n_modes"]), int(g["nt"]), int(g["seed"]), cplx)
+        base = o.FlowOracle.reconstruct(modes, coeffs, g["ltm"])
+        assert np.abs(base[::2, ::3, ::4, :] - g[tag + "_base_sample"]).max() < 1e-13
+        assert np.abs(base.sum(axis=(1, 2)) - g[tag + "_base_plane_sum"]).max() < 1e-9
+        assert np.abs(base[-1] - g[tag + "_base_last"]).max() < 1e-13
+        flow = o.FlowOracle(base, float(g[tag + "_baseDx"]), float(g[tag + "_baseDy"]), float(g[tag + "_baseDt"]))
+        up, vp, ti, base_ti = flow.intensity()
+        assert np.abs(up - g[tag + "_uPrime"]).max() < 1e-13 and np.abs(vp - g[tag + "_vPrime"]).max() < 1e-13
+        assert np.abs(ti - g[tag + "_TI"]).max() < 1e-13 and abs(base_ti - float(g[tag + "_baseTI"])) < 1e-13
+        flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
+        assert rel_err(flow.interp(g[tag + "_interp_t"], g[tag + "_interp_xy"]), g[tag + "_interp_res"]) < 1e-12
+
+
+def test_replay_buffer_oracle_vs_reference_class():
+    """oracle.ReplayBufferOracle against the arrays left behind by the UNMODIFIED CustomReplayBuffer
+    (main_02_sbl_contrib_customBuffer.py:57-160; tests/golden/gen_golden_replay.py), add by add."""
+    g = load_golden("replay")
+    buf = o.ReplayBufferOracle(int(g["buffer_size_arg"]), int(g["n_envs"]))
+    assert buf.buffer_size == int(g["slots"])
+    for k in range(g["in_obs"].shape[0]):
+        buf.add(g["in_obs"][k], g["in_next_obs"][k], g["in_act"][k], g["in_rew"][k], g["in_done"][k], g["in_timeout"][k])
+        assert (buf.pos, int(buf.full), buf.nRollovers) == tuple(g["trace"][k])
+    for name in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        assert np.array_equal(getattr(buf, name), g["buf_" + name]), name
+
+
 def test_heading_error_legacy():
     g = load_golden("legacy")
     got = o.angle_error(g["heading_pairs"][:, 0], g["heading_pairs"][:, 1])

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from conftest import load_golden
+from oracle import oracle_np as o
 
 pytestmark = pytest.mark.gpu
 
@@ -108,38 +109,42 @@ def test_sb3_vecenv_protocol_and_monitor_csv(tmp_path):
     assert venv.env_is_wrapped(object) == [False] * 16 and venv.get_attr("num_envs") == [16] * 16
 
 
-def test_symmetry_replay_buffer_matches_upstream_semantics():
-    """Against a numpy restatement of CustomReplayBuffer.add (main_02_sbl_contrib_customBuffer.py:57-160)."""
-    T_OBS = np.array([[1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], [-1, -1, 1, 1, -1, -1, -1, -1, 1, 1, 1], [-1, 1, 1, 1, -1, 1, -1, 1, 1, 1, 1],
-                      [1, -1, 1, 1, 1, -1, 1, -1, 1, 1, 1], [1, 1, -1, 1, 1, 1, 1, 1, -1, 1, 1]], dtype=np.float32)
-    T_ACT = np.array([[1, 1, 1], [-1, -1, 1], [-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=np.float32)
-    n, size = 37, 23
-    ref = {"o": np.zeros((size, n, 11), np.float32), "n": np.zeros((size, n, 11), np.float32), "a": np.zeros((size, n, 3), np.float32),
-           "r": np.zeros((size, n), np.float32), "d": np.zeros((size, n), np.uint8), "pos": 0, "full": False, "roll": 0}
+def test_symmetry_replay_buffer_vs_reference_class():
+    """Against the arrays the UNMODIFIED reference class ``CustomReplayBuffer`` (main_02_sbl_contrib_customBuffer.py:57-160)
+    left behind on the same sequence of ``add`` calls (tests/golden/gen_golden_replay.py: 34 adds into 23 slots of 5 envs,
+    past the third roll-over, with ``TimeLimit.truncated`` infos): slot bookkeeping after every add, final contents bitwise."""
+    g = load_golden("replay")
+    n, ld = int(g["n_envs"]), 32
+    buf = vec_tools.SymmetryReplayBuffer(int(g["buffer_size_arg"]), n, dtype=torch.float32, device=DEV)
+    assert buf.buffer_size == int(g["slots"])            # SB3: transitions // n_envs
+    fm = lambda x: torch.as_tensor(np.pad(np.atleast_2d(x.T), ((0, 0), (0, ld - n))), device=DEV).contiguous()
+    for k in range(g["in_obs"].shape[0]):
+        rew = torch.as_tensor(np.pad(g["in_rew"][k], (0, ld - n)), device=DEV)
+        done = torch.as_tensor(np.pad(g["in_done"][k].astype(np.uint8), (0, ld - n)), device=DEV)
+        infos = [({"TimeLimit.truncated": True} if t else {}) for t in g["in_timeout"][k]]      # as VecEnv.step returns them
+        buf.add(fm(g["in_obs"][k]), fm(g["in_next_obs"][k]), fm(g["in_act"][k]), rew, done, infos)
+        assert (buf.pos, int(buf.full), buf.nRollovers) == tuple(g["trace"][k]), k
+    for name in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        got = getattr(buf, name).cpu().numpy().astype(np.float32)
+        assert np.array_equal(got, g["buf_" + name]), name
 
-    def ref_add(o, no, a, r, d):
-        for i in range(5):
-            if ref["roll"] > 2 and i != 0:
-                continue
-            p = ref["pos"]
-            ref["o"][p], ref["n"][p], ref["a"][p], ref["r"][p], ref["d"][p] = o * T_OBS[i], no * T_OBS[i], a * T_ACT[i], r, d
-            ref["pos"] += 1
-            if ref["pos"] == size:
-                ref["full"], ref["pos"] = True, 0
-                ref["roll"] += 1
 
-    buf = vec_tools.SymmetryReplayBuffer(size, n, dtype=torch.float32, device=DEV)
+def test_symmetry_replay_buffer_vs_oracle_larger_batch():
+    """A batch that is not a multiple of anything (37 envs, padded rows), fp64, no timeouts, against oracle.ReplayBufferOracle
+    (itself pinned to the reference class on the CPU side)."""
+    n, slots, ld = 37, 23, 64
+    ref = o.ReplayBufferOracle(slots * n, n, dtype=np.float64)
+    buf = vec_tools.SymmetryReplayBuffer(slots * n, n, dtype=torch.float64, device=DEV)
     rng = np.random.default_rng(0)
-    ld = 64
     for k in range(30):
-        o, no, a = rng.uniform(-1, 1, (n, 11)).astype(np.float32), rng.uniform(-1, 1, (n, 11)).astype(np.float32), rng.uniform(-1, 1, (n, 3)).astype(np.float32)
-        r, d = rng.uniform(-3, 3, n).astype(np.float32), (rng.uniform(size=n) < 0.1).astype(np.uint8)
-        ref_add(o, no, a, r, d)
-        fm = lambda x, kdim: torch.as_tensor(np.pad(x.T, ((0, 0), (0, ld - n))), device=DEV).contiguous()
-        buf.add(fm(o, 11), fm(no, 11), fm(a, 3), torch.as_tensor(np.pad(r, (0, ld - n)), device=DEV), torch.as_tensor(np.pad(d, (0, ld - n)), device=DEV))
-        assert (buf.pos, buf.full, buf.nRollovers) == (ref["pos"], ref["full"], ref["roll"])
+        ob, no, a = rng.uniform(-1, 1, (n, 11)), rng.uniform(-1, 1, (n, 11)), rng.uniform(-1, 1, (n, 3))
+        r, d = rng.uniform(-3, 3, n), (rng.uniform(size=n) < 0.1).astype(np.uint8)
+        ref.add(ob, no, a, r, d)
+        fm = lambda x: torch.as_tensor(np.pad(x.T, ((0, 0), (0, ld - n))), device=DEV).contiguous()
+        buf.add(fm(ob), fm(no), fm(a), torch.as_tensor(np.pad(r, (0, ld - n)), device=DEV), torch.as_tensor(np.pad(d, (0, ld - n)), device=DEV))
+        assert (buf.pos, buf.full, buf.nRollovers) == (ref.pos, ref.full, ref.nRollovers)
     assert buf.nRollovers > 2   # both regimes (with and without mirror images) were exercised
-    for key, t in (("o", buf.observations), ("n", buf.next_observations), ("a", buf.actions), ("r", buf.rewards), ("d", buf.dones)):
-        assert np.array_equal(t.cpu().numpy(), ref[key]), key
+    for name in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        assert np.array_equal(getattr(buf, name).cpu().numpy().astype(np.float64), getattr(ref, name)), name
     s = buf.sample(256)
     assert s["observations"].shape == (256, 11) and s["actions"].shape == (256, 3) and s["dones"].dtype == torch.uint8
