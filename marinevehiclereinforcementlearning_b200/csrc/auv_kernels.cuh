@@ -483,68 +483,97 @@ __global__ void flow_scale_kernel(long cells, const T* base, T* out, int nc_out,
 // ReconstructedFlow.__init__ (flowGenerator.py:15-23): baseFlowData[t] = Re(modes @ coeffs[:, t]) + lt_mean, written as
 // ONE pass in the layout and precision the env reads: out T [nt][P] (P = Ny * Nx * 3 values of a plane), accumulated in
 // fp64 like the reference's numpy matmul.  modes [P][K] and coeffs [K][nt] are fp64, complex (interleaved re, im: the
-// pySPOD blobs are complex128) or real; only the real part of the product is formed (2 of the 4 real products), the mean is
-// added and the result converted in the epilogue - no [P][nt] intermediate, no transpose, no separate "+ mean" pass.
-// 64 x 64 output tile per CTA, 16 x 16 threads with a 4 x 4 micro-tile each, K in steps of 16 through shared memory.
+// pySPOD blobs are complex128) or real.
+//
+// This is the one dense contraction of the code base, so it runs on the tensor cores: fp64 has no tcgen05 / TMEM path, the
+// fp64 tensor-core instruction of sm_100 is the warp-level DMMA (mma.sync.m8n8k4.f64).  Only the real part is wanted:
+// Re(m c) = mr cr - mi ci is ONE real GEMM of depth 2K over the interleaved storage, A'[p][2k + s] = modes' raw doubles
+// and B'[2k + s][t] = (cr, -ci) - half the arithmetic of the complex product a library ZGEMM forms and then discards.
+// CTA = 128 (p) x 64 (t) outputs, 8 warps of 32 x 32 (4 x 4 DMMA tiles, 32 fp64 accumulators per thread), depth in steps of
+// 16 through shared memory (padded: both fragment loads are conflict-free), next tiles prefetched into registers while the
+// current ones are multiplied; mean, conversion to T and the [nt][P] layout are fused into the epilogue - no [P][nt]
+// intermediate, no transpose, no separate "+ mean" pass.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 flow_reconstruct_kernel(long P, int K, int nt, const double* __restrict__ modes, int modes_complex, const double* __restrict__ coeffs,
                         int coeffs_complex, const double* __restrict__ mean, T* __restrict__ out) {
-    constexpr int BM = 64, BN = 64, BK = 16;
-    __shared__ double a_re[BK][BM], a_im[BK][BM], b_re[BK][BN], b_im[BK][BN];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    constexpr int BM = 128, BN = 64, BK = 16, LDA = BK + 4, LDB = BN + 8;
+    __shared__ double a_s[BM][LDA];    // A'[p][k']: rows 20 doubles apart -> the 8 x 4 fragment read (8 rows x 4 consecutive) hits 32 distinct 8-byte banks
+    __shared__ double b_s[BK][LDB];    // B'[k'][t]: rows 72 doubles apart -> the 4 x 8 fragment read likewise
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;     // this warp's 32 x 32 corner inside the CTA tile
     const long p0 = (long)blockIdx.x * BM;
     const int t0 = blockIdx.y * BN;
     const int ms = modes_complex ? 2 : 1, cs = coeffs_complex ? 2 : 1;
-    const bool imag = modes_complex && coeffs_complex;   // Re(m c) = mr cr - mi ci: the second product exists only then
-    double acc[4][4];
+    const int depth = (modes_complex && coeffs_complex) ? 2 : 1;   // real depth per mode: (re, im) pairs only when both are complex
+    const int KD = K * depth;
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
+    // global -> register staging: A' 128 x 16 = 8 doubles per thread (row = tid / 2, 8 consecutive k'), B' 16 x 64 = 4 per thread
+    double ra[8], rb[4];
+    const int a_row = tid >> 1, a_k = (tid & 1) * 8;
+    const int b_k = tid >> 4, b_t = (tid & 15) * 4;
+    auto fetch = [&](int k0) {
+        const long p = p0 + a_row;
 #pragma unroll
-        for (int e = threadIdx.x; e < BM * BK; e += 256) {   // modes: k contiguous
-            const int kk = e % BK, pp = e / BK;
-            const long p = p0 + pp; const int k = k0 + kk;
-            const bool in = p < P && k < K;
-            const double* q = modes + (p * K + k) * ms;
-            a_re[kk][pp] = in ? q[0] : 0.;
-            a_im[kk][pp] = (in && imag) ? q[1] : 0.;
+        for (int e = 0; e < 8; ++e) {
+            const int kd = k0 + a_k + e;
+            const int k = kd / depth, sft = kd - k * depth;
+            ra[e] = (p < P && kd < KD) ? modes[(p * K + k) * ms + sft] : 0.;
         }
+        const int kd = k0 + b_k;
+        const int k = kd / depth, sft = kd - k * depth;
 #pragma unroll
-        for (int e = threadIdx.x; e < BN * BK; e += 256) {   // coeffs: t contiguous
-            const int tt = e % BN, kk = e / BN;
-            const int t = t0 + tt, k = k0 + kk;
-            const bool in = t < nt && k < K;
-            const double* q = coeffs + ((long)k * nt + t) * cs;
-            b_re[kk][tt] = in ? q[0] : 0.;
-            b_im[kk][tt] = (in && imag) ? q[1] : 0.;
+        for (int e = 0; e < 4; ++e) {
+            const int t = t0 + b_t + e;
+            const double v = (t < nt && kd < KD) ? coeffs[((long)k * nt + t) * cs + sft] : 0.;
+            rb[e] = sft ? -v : v;                               // Re(m c) = mr cr - mi ci
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < KD; k0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a_s[a_row][a_k + e] = ra[e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b_s[b_k][b_t + e] = rb[e];
         __syncthreads();
+        if (k0 + BK < KD) fetch(k0 + BK);                       // in flight while the tensor cores work on this tile
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double ar[4], ai[4], br[4], bi[4];
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ar[i] = a_re[kk][tx + 16 * i]; ai[i] = a_im[kk][tx + 16 * i]; }
+            for (int i = 0; i < 4; ++i) af[i] = a_s[wm + 8 * i + g][kk + tig];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { br[j] = b_re[kk][ty + 16 * j]; bi[j] = b_im[kk][ty + 16 * j]; }
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[kk + tig][wn + 8 * j + g];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(-ai[i], bi[j], fma(ar[i], br[j], acc[i][j]));
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j], af[i], bf[j]);
         }
         __syncthreads();
     }
+    // accumulator fragment: row (p) = g, columns (t) = 2 tig, 2 tig + 1; the 8 g-lanes of a column write 8 consecutive p
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int t = t0 + ty + 16 * j;
-        if (t >= nt) continue;
+    for (int i = 0; i < 4; ++i) {
+        const long p = p0 + wm + 8 * i + g;
+        if (p >= P) continue;
+        const double mu = mean[p];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long p = p0 + tx + 16 * i;
-            if (p < P) out[(long)t * P + p] = T(acc[i][j] + mean[p]);   // consecutive threads -> consecutive p: coalesced rows
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int t = t0 + wn + 8 * j + 2 * tig + c;
+                if (t < nt) out[(long)t * P + p] = T(acc[i][j][c] + mu);
+            }
         }
     }
 }

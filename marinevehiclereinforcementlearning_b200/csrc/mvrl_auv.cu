@@ -179,7 +179,7 @@ extern "C" MVRL_API int mvrl_flow_reconstruct(int dtype, int64_t plane, int n_mo
     MVRL_ON_DEVICE_OF(out, modes, "mvrl_flow_reconstruct");
     if (mvrl_device_of(coeffs) != mvrl_dev_out_ || mvrl_device_of(mean) != mvrl_dev_out_)
         return mvrl_fail(MVRL_EINVAL, "mvrl_flow_reconstruct: coeffs / mean are not on the output's device");
-    const dim3 grid((unsigned)((plane + 63) / 64), (unsigned)((nt + 63) / 64));
+    const dim3 grid((unsigned)((plane + 127) / 128), (unsigned)((nt + 63) / 64));
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == MVRL_F64) flow_reconstruct_kernel<double><<<grid, 256, 0, s>>>(plane, n_modes, nt, modes, modes_complex, coeffs, coeffs_complex, mean, (double*)out);
     else flow_reconstruct_kernel<float><<<grid, 256, 0, s>>>(plane, n_modes, nt, modes, modes_complex, coeffs, coeffs_complex, mean, (float*)out);
