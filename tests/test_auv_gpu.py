@@ -371,3 +371,4 @@ def test_auv_one_step_local_error_all_envs(dtype):
     assert n_cmp >= 0.995 * n_all
     assert worst_obs <= tol and worst_rew <= tol, (worst_obs, worst_rew)
 
+
