@@ -278,6 +278,10 @@ class SymmetryReplayBuffer:
     def __init__(self, buffer_size, n_envs, dtype=torch.float32, device="cuda", ld=None):
         self.n_envs = int(n_envs)
         self.buffer_size = max(int(buffer_size) // self.n_envs, 1)
+        if self.buffer_size < self.N_TRANSFORMS:
+            # upstream would overwrite the same slot several times within one add(); the five images of an add are written
+            # by one launch here, so they need five distinct slots
+            raise ValueError("buffer_size // n_envs = %d slots: need at least %d (one per mirror image)" % (self.buffer_size, self.N_TRANSFORMS))
         self.dtype, self.device = dtype, torch.device(device)
         self.ld = int(ld) if ld is not None else self.n_envs
         z = lambda *shape, dt=dtype: torch.zeros(shape, dtype=dt, device=self.device)

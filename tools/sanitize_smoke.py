@@ -49,7 +49,7 @@ for n in (1, 31, 130, 257):
             os.environ["MVRL_AUV_NO_STAGE"] = stage
             ea = AuvVecEnv(n, flow, dtype=dtype, maxSteps=4, auto_reset=True, noiseMagCoeffs=0.1, record_aux=True)
             prev = ea.reset().T.contiguous()
-            buf = vec_tools.SymmetryReplayBuffer(7, n, dtype=dtype, device=dev)
+            buf = vec_tools.SymmetryReplayBuffer(7 * n, n, dtype=dtype, device=dev)   # 7 slots of n transitions
             ea._state[0, : max(1, n // 3)] = float("nan")
             for k in range(6):
                 act = torch.as_tensor(rng.uniform(-1, 1, (n, 3)), dtype=dtype, device=dev)
