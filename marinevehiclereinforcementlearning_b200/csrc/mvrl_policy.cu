@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -23,6 +24,13 @@
 #include "mvrl_math.cuh"
 
 using namespace mvrl;
+
+#ifndef MVRL_POLICY_PREFETCH
+#define MVRL_POLICY_PREFETCH 1
+#endif
+#ifndef MVRL_POLICY_STAGGER_NS
+#define MVRL_POLICY_STAGGER_NS 0
+#endif
 
 namespace {
 
@@ -131,21 +139,40 @@ __global__ void __launch_bounds__(THREADS, 2) policy_act_kernel(const __grid_con
     const float* bias = reinterpret_cast<const float*>(smem + OFF_B);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const long n_tiles = (a.n + TILE - 1) / TILE;
+    // the observation rows of this thread's two environments (k = 2t, 2t + 1, 2t + 8, 2t + 9), already packed as the layer-1
+    // A fragment; fetched one tile AHEAD: the loads of tile i + 1 are in flight while tile i runs through the network
+    // (loaded at the top of the tile they cost a DRAM / L2 round trip per tile: long_scoreboard 2.7 per issue)
+    auto load_obs = [&](long tile, unsigned (&a1)[4]) {
+        const long r0 = tile * TILE + warp * 16 + g, r1 = r0 + 8;
+        const bool ok0 = tile < n_tiles && r0 < a.n, ok1 = tile < n_tiles && r1 < a.n;
+        float x[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 2 * t + (j & 1) + (j >> 1) * 8;
+            const bool kv = k < a.obs_dim;
+            x[0][j] = (kv && ok0) ? a.obs[(long)k * a.ld + r0] : 0.0f;
+            x[1][j] = (kv && ok1) ? a.obs[(long)k * a.ld + r1] : 0.0f;
+        }
+        a1[0] = pack_bf16(x[0][0], x[0][1]); a1[1] = pack_bf16(x[1][0], x[1][1]);
+        a1[2] = pack_bf16(x[0][2], x[0][3]); a1[3] = pack_bf16(x[1][2], x[1][3]);
+    };
+#if MVRL_POLICY_STAGGER_NS > 0
+    // the warps of a scheduler start in lock step and every tile takes the same time, so their shared-memory / tensor-core
+    // phases and their activation (MUFU / FMA) phases coincide instead of overlapping: start them a quarter tile apart
+    __nanosleep((unsigned)(((warp >> 2) + 2 * (blockIdx.x >= gridDim.x / 2 ? 1 : 0)) * MVRL_POLICY_STAGGER_NS));
+#endif
+    unsigned a_next[4];
+    load_obs(blockIdx.x, a_next);
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long r0 = tile * TILE + warp * 16 + g, r1 = r0 + 8;
         const bool ok0 = r0 < a.n, ok1 = r1 < a.n;
-        // ---- layer 1: the observation rows of this thread's two environments, k = 2t, 2t + 1, 2t + 8, 2t + 9
+        // ---- layer 1
         unsigned afr[8][4];
         {
-            float x[2][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 2 * t + (j & 1) + (j >> 1) * 8;
-                const bool kv = k < a.obs_dim;
-                x[0][j] = (kv && ok0) ? a.obs[(long)k * a.ld + r0] : 0.0f;
-                x[1][j] = (kv && ok1) ? a.obs[(long)k * a.ld + r1] : 0.0f;
-            }
-            const unsigned a1[4] = {pack_bf16(x[0][0], x[0][1]), pack_bf16(x[1][0], x[1][1]), pack_bf16(x[0][2], x[0][3]), pack_bf16(x[1][2], x[1][3])};
+            const unsigned a1[4] = {a_next[0], a_next[1], a_next[2], a_next[3]};
+#if MVRL_POLICY_PREFETCH
+            load_obs(tile + gridDim.x, a_next);
+#endif
             float acc[16][4];
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt) {
@@ -202,6 +229,9 @@ __global__ void __launch_bounds__(THREADS, 2) policy_act_kernel(const __grid_con
             if (ok0) a.logp[r0] = lp0 + a.logp_const;
             if (ok1) a.logp[r1] = lp1 + a.logp_const;
         }
+#if !MVRL_POLICY_PREFETCH
+        load_obs(tile + gridDim.x, a_next);
+#endif
     }
 }
 
@@ -228,11 +258,271 @@ void pack_b_fragments(const float* W, int N, int K, int n_tiles, int k_steps, un
             }
 }
 
+
+// =====================================================================================================================
+// tcgen05 version of the same network (the default): CTA tile = 128 environments = the 128 lanes of tensor memory.
+// Per layer ONE thread issues tcgen05.mma (M = 128, N = 128, K = 16 per instruction, bf16 operands from shared memory
+// through matrix descriptors, fp32 accumulator in TMEM), commits to an mbarrier; the four warps then read their lane
+// quadrant of the accumulator with tcgen05.ld (thread = one environment's row), add the bias, apply GELU, pack to bf16 and
+// store the row into the A operand of the next layer - in the canonical K-major core-matrix layout (8 rows x 16 bytes
+// contiguous; LBO = 128 B between the K-chunks, SBO = (K / 8) * 128 B between 8-row groups; no swizzle), so the
+// store of 8 consecutive lanes is one contiguous 128-byte line.  Weights sit in shared memory in the same layout
+// (packed on the host), read by the tensor core ONCE per 128-row tile - the mma.sync version re-reads every B fragment
+// for each 16 rows, 587 MB of shared-memory traffic per launch, its largest single cost.  2 CTAs per SM (106 KB of
+// shared memory, 128 TMEM columns each): while one CTA's MMA runs, the other's epilogue keeps the MUFU / FMA pipes busy.
+// (First version.  Now: ONE CTA per SM with GROUPS warpgroups, each running this protocol on its own tile - see the kernel.)
+// Same bf16 operand rounding, same GELU code, same Philox streams as the mma.sync kernel (kept below it for A/B:
+// MVRL_POLICY_MMA_SYNC=1); only the fp32 summation order inside the tensor core differs.
+// =====================================================================================================================
+namespace tc5 {
+
+constexpr int TM = 128;                       // environments per tile
+constexpr int HEAD_N = 16;                    // action columns padded to the smallest N of an M = 128 MMA
+constexpr int OFF_W1 = 0;                     // [128 x 16]  bf16, canonical K-major
+constexpr int OFF_W2 = OFF_W1 + H * KIN * 2;  // [128 x 128]
+constexpr int OFF_W3 = OFF_W2 + H * H * 2;
+constexpr int OFF_W4 = OFF_W3 + H * H * 2;    // [16 x 128]
+constexpr int OFF_B = OFF_W4 + HEAD_N * H * 2;                  // float b1[128] b2[128] b3[128] b4[8] std[8]
+constexpr int PARAM_BYTES = OFF_B + (3 * H + 2 * NOUT) * 4;
+constexpr int OFF_A = (PARAM_BYTES + 127) / 128 * 128;          // activations [128 x 128] bf16 per warpgroup, canonical K-major
+constexpr int A_BYTES = TM * H * 2;
+#ifndef MVRL_POLICY_GROUPS
+#define MVRL_POLICY_GROUPS 4     // warpgroups (= tiles in flight) per CTA; one CTA per SM
+#endif
+constexpr int GROUPS = MVRL_POLICY_GROUPS;
+constexpr int SMEM_BYTES = OFF_A + GROUPS * A_BYTES;
+constexpr int TMEM_COLS = GROUPS * H <= 128 ? 128 : (GROUPS * H <= 256 ? 256 : 512);
+static_assert(GROUPS >= 1 && GROUPS * H <= 512 && SMEM_BYTES <= 227 * 1024, "warpgroups per CTA limited by TMEM columns and shared memory");
+static_assert(PARAM_BYTES % 16 == 0, "parameter block is copied with 16-byte accesses");
+
+__device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    // SM100 shared-memory matrix descriptor: start address, leading / stride byte offsets (all >> 4), version 1, no swizzle
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo >> 4) << 16) | ((unsigned long long)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor of kind::f16: fp32 accumulator, bf16 A and B, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr unsigned instr_desc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+
+#ifndef MVRL_POLICY_SPLIT
+#define MVRL_POLICY_SPLIT 1      // threads per environment row in the epilogues (1 or 2); 2 (8 warps per tile, 64 columns each) measured slower: 34.0 vs 31.9 us
+#endif
+constexpr int SPLIT = MVRL_POLICY_SPLIT;
+constexpr int GT = TM * SPLIT;   // threads of a tile group
+static_assert(SPLIT == 1 || SPLIT == 2, "a TMEM lane quadrant is reachable from warps w and w + 4 only");
+static_assert(GT * GROUPS <= 1024, "CTA size");
+
+__global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __grid_constant__ PolicyArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mma_bars[GROUPS];
+    __shared__ __align__(8) unsigned long long weights_bar;
+    __shared__ float lp_part[GROUPS][TM];
+    __shared__ unsigned tmem_base_slot;
+    // a tile group (SPLIT x 128 threads: thread = one environment's row = one TMEM lane, SPLIT threads share a row's columns)
+    // owns one tile at a time: its own A operand buffer, accumulator columns, mbarrier and named barrier; the GROUPS groups
+    // of the CTA share only the weights and run out of phase
+    const int group = threadIdx.x / GT, gt = threadIdx.x % GT, row = gt % TM, half = gt / TM;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mma_bars[group]);
+    const unsigned wbar = (unsigned)__cvta_generic_to_shared(&weights_bar);
+    if (gt == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        if (group == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {   // 128 TMEM columns per group: the fp32 accumulator of one 128 x 128 layer (the head reuses the first 16)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // parameters: global (L2) -> shared, once per CTA, as ONE bulk copy (73 KB) that lands while the first observations are
+    // fetched and packed; every thread waits for it once, before its group's first MMA / bias read.  (Copied by the threads
+    // with 16-byte loads it was 14 % of the kernel's stall samples: nine dependent L2 round trips per thread.)
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "n"(PARAM_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(a.packed), "n"(PARAM_BYTES), "r"(wbar) : "memory");
+    }
+    const unsigned tmem_all = tmem_base_slot;
+    const unsigned tmem_d = tmem_all + (unsigned)(group * H);
+    const unsigned tmem_row = tmem_d + ((unsigned)(row & ~31) << 16);   // this warp's lane quadrant (warps w and w + 4 of a group share one)
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned a_addr = smem_base + OFF_A + group * A_BYTES;
+    const float* bias = reinterpret_cast<const float*>(smem + OFF_B);
+    unsigned char* a_buf = smem + OFF_A + group * A_BYTES;
+    unsigned char* a_row16 = a_buf + (row >> 3) * (KIN / 8 * 128) + (row & 7) * 16;   // this thread's row, K = 16 layout (SBO 256)
+    unsigned char* a_row128 = a_buf + (row >> 3) * (H / 8 * 128) + (row & 7) * 16;    // K = 128 layout (SBO 2048)
+    unsigned parity = 0;
+    // one layer's MMAs: D[128 x N] (+)= A[128 x K] B[N x K]^T, K / 16 instructions, then commit -> mbarrier
+    auto issue_layer = [&](int w_off, int K, int N) {
+        const unsigned sbo = (unsigned)(K / 8) * 128u;
+        const unsigned long long ad = smem_desc(a_addr, 128u, sbo), bd = smem_desc(smem_base + w_off, 128u, sbo);
+        const unsigned idesc = instr_desc(TM, N);
+        for (int j = 0; j < K / 16; ++j)      // a K = 16 step is two 128-byte core-matrix columns: 256 bytes = 16 descriptor units
+            mma_ss(tmem_d, ad + (unsigned long long)(16 * j), bd + (unsigned long long)(16 * j), idesc, j > 0 ? 1u : 0u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    };
+    auto wait_layer = [&]() {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        parity ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    // hand the freshly written A operand (and the drained accumulator) over to the MMA-issuing thread
+    auto publish = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory");   // this group only
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    constexpr int XW = KIN / SPLIT;           // observation components per thread: k in [half * XW, half * XW + XW)
+    // tiles are dealt out to the SMs first (tile t -> CTA t % gridDim.x), then to the groups of a CTA: every SM gets the same
+    // number of tiles +- 1 (131 072 envs: 7 or 6 per SM; dealt to groups first, 108 SMs had 8 and 40 SMs had 4)
+    const long n_tiles = (a.n + TM - 1) / TM;
+    const long tile_step = (long)gridDim.x * GROUPS;
+    const long first_tile = (long)blockIdx.x + (long)gridDim.x * group;
+    auto load_obs = [&](long tile, float (&x)[XW]) {
+        const long r = tile * TM + row;
+        const bool ok = tile < n_tiles && r < a.n;
+#pragma unroll
+        for (int k = 0; k < XW; ++k) x[k] = (ok && half * XW + k < a.obs_dim) ? a.obs[(long)(half * XW + k) * a.ld + r] : 0.0f;
+    };
+    float x[XW];
+    load_obs(first_tile, x);
+    {   // the parameter block has landed (async proxy -> visible to the tensor core and, after this wait, to this thread)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(wbar), "r"(0u) : "memory");
+    }
+    long pending_r = -1;        // SPLIT == 2: the log-prob of the previous tile waits for the other half's partial sum
+    float pending_lp = 0.0f;
+    for (long tile = first_tile; tile < n_tiles; tile += tile_step) {
+        const long r = tile * TM + row;
+        const bool ok = r < a.n;
+        // ---- this environment's observation row as the K = 16 A operand of layer 1
+#pragma unroll
+        for (int c = 0; c < XW / 8; ++c)
+            *reinterpret_cast<uint4*>(a_row16 + (half * (XW / 8) + c) * 128) = make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                                                                                         pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+        publish();
+        if (gt == 0) issue_layer(OFF_W1, KIN, H);
+        if (SPLIT == 2 && half == 0 && pending_r >= 0) {      // the barrier above made the other half's partial visible
+            a.logp[pending_r] = pending_lp + lp_part[group][row] + a.logp_const;
+            pending_r = -1;
+        }
+        load_obs(tile + tile_step, x);            // the next tile's observations travel while this tile runs through the network
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {
+            wait_layer();
+            const float* b = bias + layer * H;
+            // ---- epilogue of hidden layer `layer`: accumulator row -> bias + GELU -> bf16 -> A operand of the next layer
+#pragma unroll 1
+            for (int c0 = half * (H / SPLIT); c0 < (half + 1) * (H / SPLIT); c0 += 32) {
+                unsigned v[32];
+                tmem_ld32(tmem_row + (unsigned)c0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {     // 8 columns = one 16-byte chunk of the row
+                    unsigned pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = c0 + 8 * q + 2 * e;
+                        pk[e] = gelu_pack2(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]), *reinterpret_cast<const float2*>(b + col));
+                    }
+                    *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            publish();
+            if (gt == 0) {
+                if (layer < 2) issue_layer(layer == 0 ? OFF_W2 : OFF_W3, H, H);
+                else issue_layer(OFF_W4, H, HEAD_N);
+            }
+        }
+        // ---- head: 128 -> A columns of this environment's row, tanh mean, Gaussian sample, log-prob; the action pairs
+        // (2 pr, 2 pr + 1) of a row are dealt out to its SPLIT threads
+        wait_layer();
+        unsigned hv[16];
+        tmem_ld16(tmem_row, hv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float* b4 = bias + 3 * H;
+        const float* sd = b4 + NOUT;
+        float lp = 0.0f;
+#pragma unroll
+        for (int pr = 0; pr < NOUT / 2; ++pr) {
+            const int col = 2 * pr;
+            if (col < a.act_dim && (pr % SPLIT) == half) {
+                const bool second = col + 1 < a.act_dim;
+                const float m0 = tanh_fast(__uint_as_float(hv[col]) + b4[col]), m1 = tanh_fast(__uint_as_float(hv[col + 1]) + b4[col + 1]);
+                float2 e = make_float2(0.0f, 0.0f);
+                if (!a.deterministic) e = normal_pair(a.seed, a.env_id0 + (unsigned long long)r, a.step, (unsigned)pr);
+                const float a0 = fminf(1.0f, fmaxf(-1.0f, fmaf(sd[col], e.x, m0))), a1 = fminf(1.0f, fmaxf(-1.0f, fmaf(sd[col + 1], e.y, m1)));
+                lp += -0.5f * (e.x * e.x + (second ? e.y * e.y : 0.0f));
+                if (ok) {
+                    a.act[(long)col * a.ld + r] = a0;
+                    if (second) a.act[(long)(col + 1) * a.ld + r] = a1;
+                    if (a.mean) { a.mean[(long)col * a.ld + r] = m0; if (second) a.mean[(long)(col + 1) * a.ld + r] = m1; }
+                    if (a.eps) { a.eps[(long)col * a.ld + r] = e.x; if (second) a.eps[(long)(col + 1) * a.ld + r] = e.y; }
+                }
+            }
+        }
+        if (SPLIT == 1) {
+            if (a.logp != nullptr && ok) a.logp[r] = lp + a.logp_const;
+        } else if (half == 1) {
+            lp_part[group][row] = lp;
+        } else if (a.logp != nullptr && ok) {
+            pending_r = r; pending_lp = lp;
+        }
+        // the next tile's first publish() orders these accumulator reads before the next layer-1 MMA overwrites TMEM
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (SPLIT == 2 && half == 0 && pending_r >= 0) a.logp[pending_r] = pending_lp + lp_part[group][row] + a.logp_const;
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(TMEM_COLS) : "memory");
+}
+
+// W [N][K] (row = output unit, K contiguous: torch.nn.Linear) -> canonical K-major core-matrix order, zero padded to Np x Kp:
+// element (n, k) at bf16 index ((n / 8) * (Kp / 8) + k / 8) * 64 + (n % 8) * 8 + k % 8
+void pack_canonical(const float* W, int N, int K, int Np, int Kp, unsigned char* dst) {
+    unsigned short* out = reinterpret_cast<unsigned short*>(dst);
+    for (int n = 0; n < Np; ++n)
+        for (int k = 0; k < Kp; ++k)
+            out[((size_t)(n / 8) * (Kp / 8) + k / 8) * 64 + (n % 8) * 8 + k % 8] = (n < N && k < K) ? bf16_bits(W[(size_t)n * K + k]) : (unsigned short)0;
+}
+
+}  // namespace tc5
+
 }  // namespace
 
 struct MvrlPolicy {
     int device, obs_dim, act_dim, sm_count;
-    unsigned char* packed;   // device
+    unsigned char* packed;   // device: B fragments of the mma.sync kernel
+    unsigned char* packed5;  // device: canonical K-major matrices of the tcgen05 kernel
+    bool mma_sync;           // MVRL_POLICY_MMA_SYNC=1: the warp-level mma.sync kernel instead of tcgen05
     bool has_weights;
     float logp_const;        // -sum(log_std)
 };
@@ -245,13 +535,17 @@ extern "C" MVRL_API int mvrl_policy_create(MvrlPolicy** out, int device, int obs
     MVRL_ON_DEVICE(device);
     MvrlPolicy* h = new (std::nothrow) MvrlPolicy();
     if (!h) return mvrl_fail(MVRL_EINVAL, "out of host memory");
-    h->device = device; h->obs_dim = obs_dim; h->act_dim = act_dim; h->has_weights = false; h->logp_const = 0.f; h->packed = nullptr;
+    h->device = device; h->obs_dim = obs_dim; h->act_dim = act_dim; h->has_weights = false; h->logp_const = 0.f; h->packed = nullptr; h->packed5 = nullptr;
+    { const char* e = getenv("MVRL_POLICY_MMA_SYNC"); h->mma_sync = (e && e[0] == '1'); }
     h->sm_count = 148;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->sm_count = v; else cudaGetLastError(); }
     cudaError_t e = cudaMalloc(&h->packed, PACKED_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&h->packed5, tc5::PARAM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACKED_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc5::policy_act_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::SMEM_BYTES);
     if (e != cudaSuccess) {
         if (h->packed) cudaFree(h->packed);
+        if (h->packed5) cudaFree(h->packed5);
         delete h;
         return mvrl_fail(MVRL_ECUDA, "mvrl_policy_create: %s", cudaGetErrorString(e));
     }
@@ -261,7 +555,7 @@ extern "C" MVRL_API int mvrl_policy_create(MvrlPolicy** out, int device, int obs
 
 extern "C" MVRL_API int mvrl_policy_destroy(MvrlPolicy* h) {
     if (!h) return MVRL_OK;
-    { MvrlDeviceGuard guard(h->device); cudaFree(h->packed); }
+    { MvrlDeviceGuard guard(h->device); cudaFree(h->packed); cudaFree(h->packed5); }
     delete h;
     return MVRL_OK;
 }
@@ -281,6 +575,13 @@ extern "C" MVRL_API int mvrl_policy_set_weights(MvrlPolicy* h, const float* W1, 
     h->logp_const = (float)(-lsum);
     MVRL_ON_DEVICE(h->device);
     MVRL_CUDA(cudaMemcpy(h->packed, buf.data(), PACKED_BYTES, cudaMemcpyHostToDevice));
+    std::vector<unsigned char> buf5(tc5::PARAM_BYTES, 0);
+    tc5::pack_canonical(W1, H, h->obs_dim, H, KIN, buf5.data() + tc5::OFF_W1);
+    tc5::pack_canonical(W2, H, H, H, H, buf5.data() + tc5::OFF_W2);
+    tc5::pack_canonical(W3, H, H, H, H, buf5.data() + tc5::OFF_W3);
+    tc5::pack_canonical(W4, h->act_dim, H, tc5::HEAD_N, H, buf5.data() + tc5::OFF_W4);
+    memcpy(buf5.data() + tc5::OFF_B, fb, (3 * H + 2 * NOUT) * 4);
+    MVRL_CUDA(cudaMemcpy(h->packed5, buf5.data(), tc5::PARAM_BYTES, cudaMemcpyHostToDevice));
     h->has_weights = true;
     return MVRL_OK;
 }
@@ -299,6 +600,12 @@ extern "C" MVRL_API int mvrl_policy_act(MvrlPolicy* h, int64_t n, int64_t ld, co
     const int64_t tiles = (n + TILE - 1) / TILE;
     const int64_t cap = 2 * (int64_t)h->sm_count;
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    policy_act_kernel<<<grid, THREADS, PACKED_BYTES, (cudaStream_t)stream>>>(a);
+    if (h->mma_sync) {
+        policy_act_kernel<<<grid, THREADS, PACKED_BYTES, (cudaStream_t)stream>>>(a);
+    } else {
+        a.packed = h->packed5;
+        const int64_t cap5 = (tc5::GROUPS == 1 ? 2 : 1) * (int64_t)h->sm_count;   // small batches: one tile per SM before a second group gets one
+        tc5::policy_act_tc5_kernel<<<(unsigned)(tiles < cap5 ? tiles : cap5), tc5::GT * tc5::GROUPS, tc5::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    }
     return mvrl_check_launch("policy_act");
 }

@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, GPU call R: tcgen05 actor kernel against the mma.sync one
+O=gpurun_out/r2r; mkdir -p $O
+timeout 180 python -m pytest tests/test_policy_gpu.py -q -x > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log; tail -15 $O/pytest.log
+R="timeout 300 python bench.py --workload rollout --steps 20 --warmup 3"
+$R > $O/rollout_tc5.json 2>> $O/err.log
+MVRL_POLICY_MMA_SYNC=1 $R > $O/rollout_mma_sync.json 2>> $O/err.log
+for f in $O/rollout*.json; do python - $f <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1].split('/')[-1], '%.4g'%d['value'], '%.2f us'%(d['ms_per_step']*1e3), {k:v for k,v in d.items() if 'us' in k or 'share' in k})
+except Exception as e: print(sys.argv[1], 'failed', e)
+PY
+done
+tail -5 $O/err.log
