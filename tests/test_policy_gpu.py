@@ -89,3 +89,32 @@ def test_rollout_step_is_actor_plus_env_step():
         assert float(env.actions_fm.abs().max()) <= 1.0
     assert bool(torch.isfinite(env.systemState).all()) and bool(torch.isfinite(logp[:n]).all())
     assert env.episode_stats()["episodes"] == 2 * n
+
+
+@pytest.mark.parametrize("obs_dim,act_dim", [(9, 6), (16, 8), (5, 3), (1, 1)])
+def test_tcgen05_actor_agrees_with_the_warp_level_mma_kernel(monkeypatch, obs_dim, act_dim):
+    """Two independent implementations of the same network in the library - the default tcgen05 kernel (operands through
+    shared-memory descriptors, accumulator in tensor memory, biases added by the tensor core) and the mma.sync kernel
+    (register fragments; MVRL_POLICY_MMA_SYNC=1) - on the same inputs: identical Philox draws, means within the fp32
+    summation-order difference, log-probs equal; sizes around the 128-row tile and more tiles than tile groups."""
+    for n in (1, 127, 129, 1000, 80000):
+        pols = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("MVRL_POLICY_MMA_SYNC", flag)
+            p = MlpGaussianPolicy(obs_dim, act_dim, device=DEV, seed=3)
+            for b in p.biases:
+                b.uniform_(-0.3, 0.3, generator=torch.Generator().manual_seed(5))
+            p.log_std = torch.linspace(-1.0, 0.1, act_dim)
+            p.sync_weights()
+            pols.append(p)
+        out = []
+        for p in pols:
+            obs, act, mean, eps, logp = _buffers(p, n, seed=1)
+            p.act_into(obs, act, n, logp=logp, mean=mean, eps=eps, env_id0=5, step=9)
+            out.append((act, mean, eps, logp))
+        (a5, m5, e5, l5), (as_, ms, es, ls) = out
+        assert torch.equal(e5, es)                                             # same noise, bit for bit (also the untouched padding)
+        assert float((m5[:, :n] - ms[:, :n]).abs().max()) < 2e-3               # bf16 re-rounding of activations that differ in the last fp32 bits
+        assert float((m5[:, :n] - ms[:, :n]).abs().mean()) < 1e-4
+        assert torch.allclose(l5[:n], ls[:n], atol=1e-6)
+        assert bool((a5[:, n:] == 7.0).all()) and bool((l5[n:] == 7.0).all())  # nothing written beyond n
