@@ -569,8 +569,12 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
             "env_share": (ms_env / (rollouts * T)) / per_step,
             "env_us_per_step": 1e3 * ms_env / (rollouts * T), "policy_and_bookkeeping_us_per_step": 1e3 * (per_step - ms_env / (rollouts * T)),
             "flop_per_env_step": {"env": flop_per_env_step("setpoint", n_sub), "policy": 2 * sum(dims[i] * dims[i + 1] for i in range(4))},
-            "policy": ("MLP 9-128-128-128-6 GELU + Gaussian head as one kernel: mma.sync bf16 (fp32 accumulate), activations in registers, "
-                       "weights in shared memory, Philox sampling (csrc/mvrl_policy.cu)") if policy == "fused" else
+            "policy": (("MLP 9-128-128-128-6 GELU + Gaussian head as one kernel: warp-level mma.sync bf16 (fp32 accumulate), activations in "
+                        "registers, weights in shared memory, Philox sampling (csrc/mvrl_policy.cu, MVRL_POLICY_MMA_SYNC=1)")
+                       if os.environ.get("MVRL_POLICY_MMA_SYNC", "0") == "1" else
+                       ("MLP 9-128-128-128-6 GELU + Gaussian head as one kernel: tcgen05.mma (bf16 operands through shared-memory descriptors, "
+                        "fp32 accumulators in tensor memory, biases added by the tensor core), 128-environment tiles, 4 in flight per SM, "
+                        "Philox sampling (csrc/mvrl_policy.cu)")) if policy == "fused" else
                       "MLP 9-128-128-128-6 GELU + Gaussian head, PyTorch (cuBLASLt TF32 GEMMs with fused bias + GELU): library code",
             "stats_allreduce": "episode statistics (8 doubles) all-reduced once per rollout, inside the timed region" if world > 1 else "single rank: no collective",
             "clocks": clk, "episode_stats": holder.get("s")}
