@@ -479,7 +479,8 @@ static void drop_host_graphs(MvrlRov6* h) {
 
 // Piece boundaries of the host pipeline: `chunks` equal pieces (0: kDefaultChunks for large batches), multiples of the 256-environment
 // transpose tile.  Measured on B200 / PCIe gen5 (r1o, r1p): 4 pieces 0.90e9, 6 0.99e9, 8 1.02e9, 12 1.01e9, 16 0.95e9
-// env-steps/s; geometric ramps (small first piece, growing later ones) were all slower than 8 equal pieces.
+// env-steps/s; geometric ramps (small first piece, growing later ones) were all slower than 8 equal pieces, and so were tapered
+// plans with a smaller first AND last piece (r2y: 9-12 pieces, end pieces 0.25-0.5 of the others: 0.94-1.08e9 vs 1.085e9).
 static constexpr int kDefaultChunks = 8;
 static int host_chunk_plan(int64_t n, int chunks, int64_t* first /* [kMaxChunks + 1] */) {
     if (chunks <= 0) {   // default: 8 pieces, but none smaller than 64 Ki environments (a piece costs ~6 us of fixed overhead)
