@@ -363,7 +363,10 @@ MVRL_API int mvrl_replay_add_symmetric(int dtype, int64_t n, int64_t ld, const v
  * mean / eps (nullable) [act_dim][ld] for the learner and the tests; deterministic != 0 returns the mean (SB3
  * predict(obs, deterministic=True)).  Operands are bf16 (fp32 accumulate), GELU in its tanh form (torch gelu(approximate=
  * "tanh")).  fp32 only; obs_dim <= 16, act_dim <= 8, hidden width 128.  set_weights takes HOST arrays in torch.nn.Linear layout
- * (W [out][in]) and synchronises; act launches on the caller's stream and does not synchronise. */
+ * (W [out][in]) and synchronises; act launches on the caller's stream and does not synchronise.  The kernel is written for the
+ * sm_100a tensor core (tcgen05.mma from shared-memory descriptors, accumulators in tensor memory; one CTA per SM takes all 512
+ * TMEM columns while it runs); MVRL_POLICY_MMA_SYNC=1 in the environment of mvrl_policy_create selects the warp-level mma.sync
+ * implementation of the same network instead (same noise bit for bit, means within the fp32 summation order). */
 typedef struct MvrlPolicy MvrlPolicy;
 MVRL_API int mvrl_policy_create(MvrlPolicy** out, int device, int obs_dim, int act_dim);
 MVRL_API int mvrl_policy_destroy(MvrlPolicy* h);

@@ -4,7 +4,7 @@ head, evaluated by ONE tensor-core kernel (``mvrl_policy_act``, csrc/mvrl_policy
 structure-of-arrays observation / action buffers - so that collecting a rollout step is two launches: actor, env step.
 
 The parameters live in ordinary fp32 torch tensors (a learner may update them in place); ``sync_weights()`` repacks them
-into the kernel's bf16 fragment layout.  The learner side (losses, optimiser) is out of scope, like in SURVEY.md 8(e)."""
+into the kernel's bf16 operand layout (canonical K-major core matrices for tcgen05.mma).  The learner side (losses, optimiser) is out of scope, like in SURVEY.md 8(e)."""
 import ctypes as C
 import math
 
