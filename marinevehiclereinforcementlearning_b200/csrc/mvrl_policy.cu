@@ -341,6 +341,9 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
                  : "r"(taddr) : "memory");
 }
 
+#ifndef MVRL_POLICY_PINGPONG
+#define MVRL_POLICY_PINGPONG 1   // the two pairs of tile groups take turns in the epilogue (see the kernel)
+#endif
 #ifndef MVRL_POLICY_SPLIT
 #define MVRL_POLICY_SPLIT 1      // threads per environment row in the epilogues (1 or 2); 2 (8 warps per tile, 64 columns each) measured slower: 34.0 vs 31.9 us
 #endif
@@ -439,7 +442,35 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
     }
     long pending_r = -1;        // SPLIT == 2: the log-prob of the previous tile waits for the other half's partial sum
     float pending_lp = 0.0f;
-    for (long tile = first_tile; tile < n_tiles; tile += tile_step) {
+    // PING-PONG.  Left alone, the four groups of a CTA run in lock step: they share the XU pipe fairly, so their epilogues
+    // end together, their MMAs are issued together and queue on the one tensor core (each group then waits ~2000 cycles for
+    // 576 cycles of MMA), and the XU pipe idles meanwhile - a third of a tile's 21.5 k cycles was MMA wait (clock64 trace,
+    // tools/exp/actor_trace.py).  So the groups are split into two pairs that take turns: a pair enters a hidden-layer
+    // epilogue only when the other pair has left its own (two named barriers, bar.sync by the pair that waits, bar.arrive by
+    // the pair that leaves) - while one pair keeps the XU pipe busy, the other pair's MMAs run and complete.  Every group
+    // goes through the same number of turns; a group without a tile in an iteration just passes the turn on.
+    constexpr bool PINGPONG = (MVRL_POLICY_PINGPONG != 0) && GROUPS == 4 && SPLIT == 1;
+    const int pair = group >> 1;
+    const long tiles_cta = (long)blockIdx.x < n_tiles ? (n_tiles - 1 - (long)blockIdx.x) / (long)gridDim.x + 1 : 0;   // tiles dealt to this CTA
+    const long iters = PINGPONG ? (tiles_cta + GROUPS - 1) / GROUPS : (tiles_cta > group ? (tiles_cta - group + GROUPS - 1) / GROUPS : 0);
+    long turn = 0;
+    const long turns = 3 * iters;
+    auto enter_epilogue = [&]() {
+        if (PINGPONG) asm volatile("bar.sync %0, %1;" ::"r"(5 + pair), "n"(2 * GT * 2) : "memory");
+    };
+    auto leave_epilogue = [&]() {
+        if (PINGPONG) {
+            ++turn;
+            if (!(pair == 1 && turn == turns)) asm volatile("bar.arrive %0, %1;" ::"r"(5 + (pair ^ 1)), "n"(2 * GT * 2) : "memory");
+        }
+    };
+    if (PINGPONG && pair == 1 && turns > 0) asm volatile("bar.arrive %0, %1;" ::"r"(5), "n"(2 * GT * 2) : "memory");   // the first turn is pair 0's
+    for (long it = 0; it < iters; ++it) {
+        const long tile = first_tile + it * tile_step;
+        if (tile >= n_tiles) {      // (ping-pong only) no tile in this iteration: pass the three turns on
+            for (int layer = 0; layer < 3; ++layer) { enter_epilogue(); leave_epilogue(); }
+            continue;
+        }
         const long r = tile * TM + row;
         const bool ok = r < a.n;
         // ---- this environment's observation row as the K = 16 A operand of layer 1
@@ -466,6 +497,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
 #pragma unroll
         for (int layer = 0; layer < 3; ++layer) {
             wait_layer();
+            enter_epilogue();
             const float* b = bias + layer * H;
             // (measured and dropped: 16-column chunks with the next tcgen05.ld in flight during the GELU of the current one, 26.1 vs
             // 25.7 us; two threads per row, 27.5 us)
@@ -487,6 +519,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
                     *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
+            leave_epilogue();
             publish();
             if (gt == 0) {
                 if (layer < 2) issue_layer(layer == 0 ? OFF_W2 : OFF_W3, H, H, OFF_BIAS + (layer + 1) * H * KIN * 2);
