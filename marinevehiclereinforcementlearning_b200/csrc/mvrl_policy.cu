@@ -448,7 +448,10 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
     // tools/exp/actor_trace.py).  So the groups are split into two pairs that take turns: a pair enters a hidden-layer
     // epilogue only when the other pair has left its own (two named barriers, bar.sync by the pair that waits, bar.arrive by
     // the pair that leaves) - while one pair keeps the XU pipe busy, the other pair's MMAs run and complete.  Every group
-    // goes through the same number of turns; a group without a tile in an iteration just passes the turn on.
+    // goes through the same number of turns; a group without a tile in an iteration just passes the turn on.  (Also measured:
+    // single groups in round-robin order with at most 1 / 2 / 3 in the epilogue at a time, by counters polled in shared memory:
+    // 29.6 / 24.8 / 25.3 us against 24.2 us for this pair scheme - tools/exp/r2ab.sh.  Named barriers cannot count: a group
+    // that runs two epilogues ahead of its waiter completes a barrier phase on its own, and the CTA dead-locks.)
     constexpr bool PINGPONG = (MVRL_POLICY_PINGPONG != 0) && GROUPS == 4 && SPLIT == 1;
     const int pair = group >> 1;
     const long tiles_cta = (long)blockIdx.x < n_tiles ? (n_tiles - 1 - (long)blockIdx.x) / (long)gridDim.x + 1 : 0;   // tiles dealt to this CTA

@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU call AB: actor - epilogues in round-robin order, at most 1 / 2 / 3 at a time (counter protocol); short timeouts
+O=gpurun_out/r2ab; mkdir -p $O
+P=$PWD/marinevehiclereinforcementlearning_b200
+for v in "" _k3 _k1; do
+  MVRL_LIB=$P/libmvrl$v.so timeout 60 python -m pytest tests/test_policy_gpu.py -q -x > $O/pytest$v.log 2>&1; echo "pytest$v rc=$?"; tail -1 $O/pytest$v.log
+done
+R="timeout 90 python bench.py --workload rollout --steps 20 --warmup 3"
+for v in "" _k3 _k1 "" _k3; do MVRL_LIB=$P/libmvrl$v.so $R > $O/rollout${v}_$RANDOM.json 2>> $O/err.log; done
+for f in $O/rollout*.json; do python - $f <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1].split('/')[-1], '%.4g'%d['value'], '%.2f us'%(d['ms_per_step']*1e3), 'policy %.2f us'%d['policy_and_bookkeeping_us_per_step'])
+except Exception as e: print(sys.argv[1], 'failed')
+PY
+done
+tail -3 $O/err.log
