@@ -345,7 +345,7 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
 #define MVRL_POLICY_PINGPONG 1   // the two pairs of tile groups take turns in the epilogue (see the kernel)
 #endif
 #ifndef MVRL_POLICY_SPLIT
-#define MVRL_POLICY_SPLIT 1      // threads per environment row in the epilogues (1 or 2); 2 (8 warps per tile, 64 columns each) measured slower: 34.0 vs 31.9 us
+#define MVRL_POLICY_SPLIT 1      // threads per environment row in the epilogues (1 or 2); 2 (8 warps per tile, 64 columns each, 64 registers) measured slower: 34.0 vs 31.9 us, and 28.8 vs 24.4 us with the turn schedule
 #endif
 constexpr int SPLIT = MVRL_POLICY_SPLIT;
 constexpr int GT = TM * SPLIT;   // threads of a tile group
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
     // single groups in round-robin order with at most 1 / 2 / 3 in the epilogue at a time, by counters polled in shared memory:
     // 29.6 / 24.8 / 25.3 us against 24.2 us for this pair scheme - tools/exp/r2ab.sh.  Named barriers cannot count: a group
     // that runs two epilogues ahead of its waiter completes a barrier phase on its own, and the CTA dead-locks.)
-    constexpr bool PINGPONG = (MVRL_POLICY_PINGPONG != 0) && GROUPS == 4 && SPLIT == 1;
+    constexpr bool PINGPONG = (MVRL_POLICY_PINGPONG != 0) && GROUPS == 4;
     const int pair = group >> 1;
     const long tiles_cta = (long)blockIdx.x < n_tiles ? (n_tiles - 1 - (long)blockIdx.x) / (long)gridDim.x + 1 : 0;   // tiles dealt to this CTA
     const long iters = PINGPONG ? (tiles_cta + GROUPS - 1) / GROUPS : (tiles_cta > group ? (tiles_cta - group + GROUPS - 1) / GROUPS : 0);
