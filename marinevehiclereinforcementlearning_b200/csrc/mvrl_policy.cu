@@ -341,6 +341,9 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
                  : "r"(taddr) : "memory");
 }
 
+#ifndef MVRL_POLICY_LDTM_PIPE
+#define MVRL_POLICY_LDTM_PIPE 1
+#endif
 #ifndef MVRL_POLICY_PINGPONG
 #define MVRL_POLICY_PINGPONG 1   // the two pairs of tile groups take turns in the epilogue (see the kernel)
 #endif
@@ -502,9 +505,39 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
             wait_layer();
             enter_epilogue();
             const float* b = bias + layer * H;
-            // (measured and dropped: 16-column chunks with the next tcgen05.ld in flight during the GELU of the current one, 26.1 vs
-            // 25.7 us; two threads per row, 27.5 us)
+            // (free-running groups did not profit from the double-buffered tcgen05.ld below, 26.1 vs 25.7 us - other warps hid the
+            // latency; with the turn schedule it is worth 5 %: 24.05 -> 22.85 us)
             // ---- epilogue of hidden layer `layer`: accumulator row -> bias + GELU -> bf16 -> A operand of the next layer
+#if MVRL_POLICY_LDTM_PIPE
+            // 16-column chunks, double-buffered: the tcgen05.ld of chunk k + 1 is in flight while chunk k goes through the GELU
+            // (tcgen05.wait::ld waits for every outstanding load of the thread, so it comes AFTER the arithmetic of chunk k).
+            // With the turn schedule only two warps per scheduler are in an epilogue, and nothing else hides the TMEM read latency.
+            {
+                constexpr int NCH = H / SPLIT / 16;
+                const int cbase = half * (H / SPLIT);
+                unsigned v[2][16];
+                tmem_ld16(tmem_row + (unsigned)cbase, v[0]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int c0 = cbase + 16 * ch;
+                    if (ch + 1 < NCH) tmem_ld16(tmem_row + (unsigned)(c0 + 16), v[(ch + 1) & 1]);
+                    const unsigned (&w)[16] = v[ch & 1];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {     // 8 columns = one 16-byte chunk of the row
+                        unsigned pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = c0 + 8 * q + 2 * e;
+                            if (BIAS_MMA) pk[e] = gelu_pack2(__uint_as_float(w[8 * q + 2 * e]), __uint_as_float(w[8 * q + 2 * e + 1]));
+                            else pk[e] = gelu_pack2(__uint_as_float(w[8 * q + 2 * e]), __uint_as_float(w[8 * q + 2 * e + 1]), *reinterpret_cast<const float2*>(b + col));
+                        }
+                        *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    if (ch + 1 < NCH) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+            }
+#else
 #pragma unroll 1
             for (int c0 = half * (H / SPLIT); c0 < (half + 1) * (H / SPLIT); c0 += 32) {
                 unsigned v[32];
@@ -522,6 +555,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
                     *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
+#endif
             leave_epilogue();
             publish();
             if (gt == 0) {
