@@ -88,6 +88,17 @@ __device__ __forceinline__ unsigned gelu_pack2(float x0, float x1, float2 b) {
     return pack_bf16(y.x, y.y);
 }
 
+// 2 gelu(x) = x (1 + tanh(u)) of two columns, bias already in the accumulator: the tcgen05 kernel stores TWICE the activation
+// and the host halves the next layer's weights (a power of two: exact in bf16 and in the fp32 accumulation, so nothing changes
+// numerically) - one packed multiply fewer per pair of columns
+__device__ __forceinline__ unsigned gelu2x_pack2(float x0, float x1) {
+    const float2 x = make_float2(x0, x1);
+    const float2 x2 = __fmul2_rn(x, x);
+    const float2 u = __fmul2_rn(x, __ffma2_rn(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f)));
+    const float2 th = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+    const float2 y = __ffma2_rn(x, th, x);
+    return pack_bf16(y.x, y.y);
+}
 __device__ __forceinline__ unsigned gelu_pack2(float x0, float x1) {   // the same without the bias (already in the accumulator)
     const float2 x = make_float2(x0, x1);
     const float2 x2 = __fmul2_rn(x, x);
@@ -529,7 +540,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int col = c0 + 8 * q + 2 * e;
-                            if (BIAS_MMA) pk[e] = gelu_pack2(__uint_as_float(w[8 * q + 2 * e]), __uint_as_float(w[8 * q + 2 * e + 1]));
+                            if (BIAS_MMA) pk[e] = gelu2x_pack2(__uint_as_float(w[8 * q + 2 * e]), __uint_as_float(w[8 * q + 2 * e + 1]));
                             else pk[e] = gelu_pack2(__uint_as_float(w[8 * q + 2 * e]), __uint_as_float(w[8 * q + 2 * e + 1]), *reinterpret_cast<const float2*>(b + col));
                         }
                         *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(GT * GROUPS, 1) policy_act_tc5_kernel(const __
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int col = c0 + 8 * q + 2 * e;
-                        if (BIAS_MMA) pk[e] = gelu_pack2(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]));
+                        if (BIAS_MMA) pk[e] = gelu2x_pack2(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]));
                         else pk[e] = gelu_pack2(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]), *reinterpret_cast<const float2*>(b + col));
                     }
                     *reinterpret_cast<uint4*>(a_row128 + ((c0 >> 3) + q) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -677,9 +688,15 @@ extern "C" MVRL_API int mvrl_policy_set_weights(MvrlPolicy* h, const float* W1, 
     MVRL_CUDA(cudaMemcpy(h->packed, buf.data(), PACKED_BYTES, cudaMemcpyHostToDevice));
     std::vector<unsigned char> buf5(tc5::PARAM_BYTES, 0);
     tc5::pack_canonical(W1, H, h->obs_dim, H, KIN, buf5.data() + tc5::OFF_W1);
-    tc5::pack_canonical(W2, H, H, H, H, buf5.data() + tc5::OFF_W2);
-    tc5::pack_canonical(W3, H, H, H, H, buf5.data() + tc5::OFF_W3);
-    tc5::pack_canonical(W4, h->act_dim, H, tc5::HEAD_N, H, buf5.data() + tc5::OFF_W4);
+    {   // the hidden activations are stored doubled (gelu2x_pack2): the layers that read them get half the weights
+        const float in_scale = tc5::BIAS_MMA ? 0.5f : 1.0f;
+        std::vector<float> w2((size_t)H * H), w3((size_t)H * H), w4((size_t)h->act_dim * H);
+        for (size_t i = 0; i < w2.size(); ++i) { w2[i] = in_scale * W2[i]; w3[i] = in_scale * W3[i]; }
+        for (size_t i = 0; i < w4.size(); ++i) w4[i] = in_scale * W4[i];
+        tc5::pack_canonical(w2.data(), H, H, H, H, buf5.data() + tc5::OFF_W2);
+        tc5::pack_canonical(w3.data(), H, H, H, H, buf5.data() + tc5::OFF_W3);
+        tc5::pack_canonical(w4.data(), h->act_dim, H, tc5::HEAD_N, H, buf5.data() + tc5::OFF_W4);
+    }
     memcpy(buf5.data() + tc5::OFF_B, fb, (3 * H + 2 * NOUT) * 4);
     if (tc5::BIAS_MMA) {   // bias blocks: b = t0 + t1 + t2 with every term a bf16 (24 mantissa bits in all: the fp32 bias), and the ones block
         const float* bs[3] = {b1, b2, b3};
