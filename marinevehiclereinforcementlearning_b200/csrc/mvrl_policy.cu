@@ -4,14 +4,17 @@
 // structure-of-arrays action buffer the step kernel reads: obs [O][ld] -> 128 -> 128 -> 128 -> A, tanh mean, a = clip(mean +
 // std * eps, -1, 1), log-prob.  A rollout step is then two launches (this kernel + the fused env step).
 //
-// This is the one dense contraction of the path, so it runs on the tensor cores: mma.sync m16n8k16 (bf16 operands, fp32
-// accumulate).  Each warp owns 16 environments; the 16 x 128 activations never leave its registers - the accumulator
-// fragment of one layer IS the A-operand fragment of the next after bias + GELU + bf16 packing (the m16n8 C layout of two
-// adjacent n-tiles coincides with the m16k16 A layout).  The weights (70 KB as bf16, pre-packed on the host in B-fragment
-// order so that a warp reads 256 contiguous bytes per mma) sit in shared memory and are loaded once per CTA; the grid is
-// persistent (2 CTAs per SM).  K = 128 per layer is far too short for a tcgen05 / TMEM pipeline to pay for its set-up
-// (one 128 x 128 x 128 tile per layer and 128 environments): the kernel is bound by the GELU (MUFU.TANH) and the
-// shared-memory operand reads, not by MMA issue.
+// This is the dense contraction next to the path, so it runs on the tensor cores.  Two implementations live in this file:
+//
+//  * policy_act_tc5_kernel (namespace tc5, the default): written for the 5th-generation tensor core - tcgen05.mma with M = 128
+//    (one tile = 128 environments = the 128 lanes of tensor memory), operands through shared-memory matrix descriptors,
+//    fp32 accumulators in TMEM, the epilogue of a layer writing the next layer's A operand.  Description above the kernel.
+//  * policy_act_kernel (MVRL_POLICY_MMA_SYNC=1): warp-level mma.sync m16n8k16; each warp owns 16 environments and the
+//    16 x 128 activations never leave its registers - the accumulator fragment of one layer IS the A-operand fragment of
+//    the next after bias + GELU + bf16 packing.  The weights (70 KB as bf16, pre-packed on the host in B-fragment order) sit
+//    in shared memory; persistent grid, 2 CTAs per SM.  It re-reads every weight fragment for each 16 rows (587 MB of
+//    shared-memory traffic per 131 072-env launch) and takes 42 us where the tcgen05 kernel takes 23; it stays as the
+//    second implementation the tests compare the default against (same bf16 rounding, GELU code and Philox streams).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cmath>
@@ -27,9 +30,6 @@ using namespace mvrl;
 
 #ifndef MVRL_POLICY_PREFETCH
 #define MVRL_POLICY_PREFETCH 1
-#endif
-#ifndef MVRL_POLICY_STAGGER_NS
-#define MVRL_POLICY_STAGGER_NS 0
 #endif
 
 namespace {
@@ -177,11 +177,6 @@ __global__ void __launch_bounds__(THREADS, 2) policy_act_kernel(const __grid_con
         a1[0] = pack_bf16(x[0][0], x[0][1]); a1[1] = pack_bf16(x[1][0], x[1][1]);
         a1[2] = pack_bf16(x[0][2], x[0][3]); a1[3] = pack_bf16(x[1][2], x[1][3]);
     };
-#if MVRL_POLICY_STAGGER_NS > 0
-    // the warps of a scheduler start in lock step and every tile takes the same time, so their shared-memory / tensor-core
-    // phases and their activation (MUFU / FMA) phases coincide instead of overlapping: start them a quarter tile apart
-    __nanosleep((unsigned)(((warp >> 2) + 2 * (blockIdx.x >= gridDim.x / 2 ? 1 : 0)) * MVRL_POLICY_STAGGER_NS));
-#endif
     unsigned a_next[4];
     load_obs(blockIdx.x, a_next);
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
