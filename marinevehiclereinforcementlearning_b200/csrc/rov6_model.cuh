@@ -362,15 +362,32 @@ __device__ __forceinline__ void body_accel(const Rov6Dev<S>& P, const Trig6<V>& 
 }
 
 // 1 / den for the clamped |den| >= 1e-6 of the kinematics
+// The bare MUFU.RCP.  1e-6 <= |den| <= 1 here, so neither the operand nor the result is subnormal and the flush-to-zero
+// form returns the same bits as __fdividef(1.0f, den) - which, in a translation unit compiled without -ftz, wraps the
+// MUFU in a subnormal-operand rescue (x 2^24, compare, two selects, x scale: 2 FMUL + FSETP + 2 FSEL per lane and RK4
+// stage = 40 of the rpm loop's 743 instructions per sub-step, 16 of them on the FMA pipe).  MVRL_RCP_FDIVIDEF=1 at
+// compile time restores the intrinsic (A/B builds).
+#ifndef MVRL_RCP_FDIVIDEF
+#define MVRL_RCP_FDIVIDEF 0
+#endif
+__device__ __forceinline__ float rcp_mufu(float den) {
+#if MVRL_RCP_FDIVIDEF
+    return __fdividef(1.0f, den);
+#else
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+    return inv;
+#endif
+}
 template <bool FAST> __device__ __forceinline__ float recip_clamped(float den) {
     // MUFU.RCP needs no special-case path here; one Newton step brings it to <= 1 ulp in the accurate mode
-    float inv = __fdividef(1.0f, den);
+    float inv = rcp_mufu(den);
     if constexpr (!FAST) inv = fmaf(inv, fmaf(-den, inv, 1.0f), inv);
     return inv;
 }
 template <bool FAST> __device__ __forceinline__ double recip_clamped(double den) { return 1.0 / den; }
 template <bool FAST> __device__ __forceinline__ F2 recip_clamped(F2 den) {
-    F2 inv = F2(__fdividef(1.0f, den.v.x), __fdividef(1.0f, den.v.y));
+    F2 inv = F2(rcp_mufu(den.v.x), rcp_mufu(den.v.y));
     if constexpr (!FAST) inv = fmaf_t(inv, fmaf_t(-den, inv, F2(1.0f)), inv);
     return inv;
 }
