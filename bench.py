@@ -335,12 +335,30 @@ def _max_over_ranks(x, dev, world):
     return float(t[0])
 
 
-def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False):
+def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False, chains=None):
     """W untimed calls of one_step(k), then EXACTLY `steps` timed ones (replayed as ONE CUDA graph unless graph=False)
-    between barrier + synchronize on both sides; CUDA events on the launching stream; returns (ms max over ranks, clocks)."""
+    between barrier + synchronize on both sides; CUDA events on the launching stream; returns (ms max over ranks, clocks).
+    chains = [f_0, f_1, ...] instead of one_step: every f_g(k) steps its own group of environments; the groups are
+    independent, so each runs its `steps` launches as its own chain on its own stream (forked from the timed stream after
+    the start event, joined before the stop event) - parallel branches of the same graph."""
     import torch
-    for k in range(warmup):
-        one_step(k)
+    streams = [torch.cuda.Stream(device=dev) for _ in chains] if chains else None
+
+    def issue(count):
+        if not chains:
+            for k in range(count):
+                one_step(k)
+            return
+        cur = torch.cuda.current_stream(dev)
+        for s, f in zip(streams, chains):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                for k in range(count):
+                    f(k)
+        for s in streams:
+            cur.wait_stream(s)
+
+    issue(warmup)
     _barrier(world)
     g = None
     if graph:
@@ -349,8 +367,7 @@ def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
-                for k in range(steps):
-                    one_step(k)
+                issue(steps)
         torch.cuda.current_stream(dev).wait_stream(side)
         g.replay()   # warm-up replay
         _barrier(world)
@@ -366,8 +383,7 @@ def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False
     if g is not None:
         g.replay()
     else:
-        for k in range(steps):
-            one_step(k)
+        issue(steps)
     e1.record()
     _barrier(world)
     t1 = time.time()
@@ -376,8 +392,12 @@ def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False
 
 
 def rov6_leg(dev, rank, world, n, mode="rpm", dtype="f32", n_sub=N_SUB, steps=50, warmup=5, env_id0=None, max_steps=MAX_STEPS,
-             fast=0, stats=True, graph=True, clocks=False, keep=False):
-    """One timed leg of the fused 6DoF step: n environments on this rank; returns rate per GPU (n / max-over-ranks time)."""
+             fast=0, stats=True, graph=True, clocks=False, keep=False, groups=1):
+    """One timed leg of the fused 6DoF step: n environments on this rank; returns rate per GPU (n / max-over-ranks time).
+    groups > 1: the environments are stepped as `groups` independent blocks (mvrl_rov6_step_range), each block a chain of
+    launches on its own stream - the analogue of the reference's SubprocVecEnv workers, which step their environments
+    without waiting for each other (legacy/script_0_checkScaling.py:23-40).  Every environment still takes exactly
+    `steps` steps; a block's prologue / epilogue then overlaps the other blocks' RK4 loops instead of idling the SMs."""
     import torch
     from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv
     tdtype = torch.float64 if dtype == "f64" else torch.float32
@@ -395,11 +415,23 @@ def rov6_leg(dev, rank, world, n, mode="rpm", dtype="f32", n_sub=N_SUB, steps=50
     def one_step(k):
         env._bufs.action = acts[k % n_act].data_ptr()
         env.step_async()
-    ms, clk = timed_launches(dev, world, one_step, steps, warmup, graph=graph, clocks=clocks)
+    chains = None
+    if groups > 1:
+        per = -(-n // groups)
+        per += per % 2                         # blocks start on an even environment (two environments per thread)
+        blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)]
+
+        def chain(first, count):
+            def f(k):
+                env._bufs.action = acts[k % n_act].data_ptr()
+                env.step_range_async(first, count)
+            return f
+        chains = [chain(lo, cnt) for lo, cnt in blocks]
+    ms, clk = timed_launches(dev, world, one_step, steps, warmup, graph=graph, clocks=clocks, chains=chains)
     w = 8 if dtype == "f64" else 4
     touched = n * bytes_per_env_step(mode, w) + n_act * na * env.ld * w
     out = {"envs_per_gpu": n, "action_mode": mode, "dtype": dtype, "n_sub": n_sub, "steps": steps, "ms_per_step": ms / steps,
-           "rate_per_gpu": n / (ms / steps * 1e-3),
+           "rate_per_gpu": n / (ms / steps * 1e-3), "stream_groups": len(chains) if chains else 1,
            "l2": "larger than L2" if touched > 126e6 else "working set %.0f MB is L2-resident (what stepping a shard of this size is)" % (touched / 1e6)}
     if clk is not None:
         out["clocks"] = clk
@@ -468,7 +500,7 @@ def rov3_leg(dev, rank, world, n, mode, n_sub=N_SUB, steps=50, warmup=5, clocks=
             "action_mode": mode, "n_sub": n_sub, "clocks": clk, "episode_stats": env.episode_stats()}
 
 
-def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, clocks=False, policy="fused"):
+def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, clocks=False, policy="fused", groups=1):
     """Config 5: rollout collection over the 6DoF env in the reference's Gym semantics (PID set-point actions) with the
     policy of legacy/main_00_sbl.py:100-105 (MLP 9-128-128-128-6, GELU) + Gaussian head; T-step rollouts replayed as one
     CUDA graph, episode statistics all-reduced once per rollout (K5, NCCL when N > 1).
@@ -494,20 +526,50 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
     if policy == "fused":
         buf_obs[0].copy_(env._obs)
 
-        def policy_step(t):
-            pol.act_into(buf_obs[t], buf_act[t], n, logp=buf_logp[t], env_id0=rank * n, step=t)
+        import ctypes as C
+        from marinevehiclereinforcementlearning_b200 import _lib
 
-        def env_step(t):   # the step kernel reads the actor's output and writes the next rollout row: no copies
+        def policy_step(t, lo=0, cnt=n):
+            if cnt == n:
+                pol.act_into(buf_obs[t], buf_act[t], n, logp=buf_logp[t], env_id0=rank * n, step=t)
+            else:   # environments [lo, lo + cnt) of the same rows: the C entry point takes plain pointers
+                o = 4 * lo
+                _lib.check(pol.lib.mvrl_policy_act(pol._h, cnt, ld, C.c_void_p(buf_obs[t].data_ptr() + o), C.c_void_p(buf_act[t].data_ptr() + o),
+                                                   C.c_void_p(buf_logp[t].data_ptr() + o), None, None, pol.seed & (2 ** 64 - 1), rank * n + lo, t, 0,
+                                                   _lib.current_stream(dev)))
+
+        def env_step(t, lo=0, cnt=n):   # the step kernel reads the actor's output and writes the next rollout row: no copies
             env._bufs.action, env._bufs.obs = buf_act[t].data_ptr(), buf_obs[t + 1].data_ptr()
             env._bufs.reward, env._bufs.done = buf_rew[t].data_ptr(), buf_done[t].data_ptr()
-            env.step_async()
+            if cnt == n:
+                env.step_async()
+            else:
+                env.step_range_async(lo, cnt)
+
+        # groups > 1: the environments are split into independent blocks, each block a chain (actor, env step) x T on its
+        # own stream - one block's actor (tensor core / XU pipe) runs beside another block's env step (FMA pipe)
+        per = -(-n // max(1, groups))
+        per += (-per) % 128                                     # whole actor tiles
+        blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)] if groups > 1 else [(0, n)]
+        streams = [torch.cuda.Stream(device=dev) for _ in blocks] if groups > 1 else []
 
         def rollout():
-            for t in range(T):
-                policy_step(t)
-                env_step(t)
+            if groups <= 1:
+                for t in range(T):
+                    policy_step(t)
+                    env_step(t)
+            else:
+                cur = torch.cuda.current_stream(dev)
+                for s, (lo, cnt) in zip(streams, blocks):
+                    s.wait_stream(cur)
+                    with torch.cuda.stream(s):
+                        for t in range(T):
+                            policy_step(t, lo, cnt)
+                            env_step(t, lo, cnt)
+                for s in streams:
+                    cur.wait_stream(s)
             buf_obs[0].copy_(buf_obs[T])   # the next rollout starts where this one ended
-        launches_per_step = 2
+        launches_per_step = 2 * len(blocks)
     else:
         Wt = [w.to(dev).T.contiguous() for w in pol.weights]         # [in, out]
         b1 = [b.to(dev) for b in pol.biases]
@@ -565,7 +627,7 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
     per_step = ms / (rollouts * T)
     dims = [9, 128, 128, 128, 6]
     return {"value": n * T * rollouts / (ms * 1e-3), "unit": UNIT + " per GPU (policy included)", "ms_per_step": per_step, "envs_per_gpu": n,
-            "rollout_len": T, "rollouts": rollouts, "policy_impl": policy, "launches_per_step": launches_per_step,
+            "rollout_len": T, "rollouts": rollouts, "policy_impl": policy, "launches_per_step": launches_per_step, "stream_groups": max(1, groups),
             "env_share": (ms_env / (rollouts * T)) / per_step,
             "env_us_per_step": 1e3 * ms_env / (rollouts * T), "policy_and_bookkeeping_us_per_step": 1e3 * (per_step - ms_env / (rollouts * T)),
             "flop_per_env_step": {"env": flop_per_env_step("setpoint", n_sub), "policy": 2 * sum(dims[i] * dims[i + 1] for i in range(4))},
@@ -598,7 +660,7 @@ def run_ours(args, rank, local_rank, world):
     w = 8 if args.dtype == "f64" else 4
     na = ACTION_DIM[mode]
     leg = rov6_leg(dev, rank, world, n, mode, args.dtype, n_sub, args.steps, args.warmup, env_id0=id0, max_steps=args.max_steps,
-                   fast=args.fast_math, stats=not args.no_stats, graph=bool(args.graph), clocks=True, keep=True)
+                   fast=args.fast_math, stats=not args.no_stats, graph=bool(args.graph), clocks=True, keep=True, groups=max(1, args.stream_groups))
     env, acts = leg["env"], leg["acts"]
     ms_per_step = leg["ms_per_step"]
     n_total = ENVS_TOTAL_STRONG if strong else world * n
@@ -712,7 +774,7 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(n, mode, args.dtype, n_sub), "envs_per_gpu": n, "envs_total": n_total, "n_sub": n_sub,
-                           "action_mode": mode, "fast_math": bool(args.fast_math), "cuda_graph": bool(args.graph),
+                           "action_mode": mode, "fast_math": bool(args.fast_math), "cuda_graph": bool(args.graph), "stream_groups": leg["stream_groups"],
                            "two_envs_per_thread_ffma2": os.environ.get("MVRL_NO_X2", "0") != "1" and args.dtype == "f32", "parallelism": "env-sharded x%d, no collective on the step path" % world,
                            "l2": leg["l2"] + " (+ 4 rotating action batches)"},
                 "roofline": roofline, "cpu_baseline": cpu,
@@ -720,7 +782,7 @@ def run_ours(args, rank, local_rank, world):
                         "chunks": e2e_pieces, "host_numa_node": numa_node, "gpu_launches_per_step": 3 * e2e_pieces,
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
                                 "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, done stored into the pinned host array by the transpose kernel; the always-zero reward does not travel)"},
-                "gpu_launches": args.steps, "clocks": leg.get("clocks"), "episode_stats": leg.get("episode_stats")}
+                "gpu_launches": args.steps * leg["stream_groups"], "clocks": leg.get("clocks"), "episode_stats": leg.get("episode_stats")}
         if strong_leg is not None:
             line["strong"] = strong_leg
         if extra:
@@ -752,12 +814,12 @@ def run_secondary(args, rank, local_rank, world):
     else:
         n = args.envs if args.envs != ENVS_PER_GPU else 131072
         rollouts = max(2, args.steps // args.rollout_len)
-        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True, policy=args.policy)
+        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True, policy=args.policy, groups=args.stream_groups)
         metric, dtype = "6DoF rollout collection env-steps/sec (policy included)", "f32 env; policy bf16 operands / fp32 accumulate (fused) or TF32 (torch)"
         cfg = {"workload": "rollout: 6DoF set-point env + MLP 9-128-128-128-6 GELU Gaussian policy, %d envs/GPU, %d-step rollouts, "
                            "nSub=%d, CUDA-graph replay, stats all-reduce per rollout" % (n, args.rollout_len, args.n_sub)}
         extra = {k: r[k] for k in ("env_share", "env_us_per_step", "policy_and_bookkeeping_us_per_step", "flop_per_env_step", "policy", "policy_impl",
-                                   "launches_per_step", "stats_allreduce")}
+                                   "launches_per_step", "stats_allreduce", "stream_groups")}
         launches = rollouts * args.rollout_len
     if rank == 0:
         line = {"metric": metric, "value": world * r["value"], "unit": UNIT, "n_gpus": world, "steps": r.get("steps", launches), "warmup": args.warmup,
@@ -793,6 +855,8 @@ def main():
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
     ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
     ap.add_argument("--bind-numa", type=int, default=1, help="1: bind each rank to the CPUs of its GPU's NUMA node (host buffers of the e2e leg)")
+    ap.add_argument("--stream-groups", type=int, default=1,
+                    help="step the environments of a rank as this many independent blocks, each a chain of launches on its own stream (default 1: one launch per step)")
     ap.add_argument("--no-stats", action="store_true", help="diagnostics: do not accumulate episode statistics in the step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
