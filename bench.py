@@ -335,28 +335,19 @@ def _max_over_ranks(x, dev, world):
     return float(t[0])
 
 
-def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False, chains=None):
+def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False, blocks=None):
     """W untimed calls of one_step(k), then EXACTLY `steps` timed ones (replayed as ONE CUDA graph unless graph=False)
     between barrier + synchronize on both sides; CUDA events on the launching stream; returns (ms max over ranks, clocks).
-    chains = [f_0, f_1, ...] instead of one_step: every f_g(k) steps its own group of environments; the groups are
-    independent, so each runs its `steps` launches as its own chain on its own stream (forked from the timed stream after
-    the start event, joined before the stop event) - parallel branches of the same graph."""
+    blocks = vec_tools.EnvBlocks: one_step(k) queues step k of every block on the block's own stream; the block streams
+    fork from the timed stream after the start event and re-join it before the stop event (parallel branches of the
+    same graph), so every environment still takes exactly `steps` steps inside the timed region."""
+    import contextlib
     import torch
-    streams = [torch.cuda.Stream(device=dev) for _ in chains] if chains else None
 
     def issue(count):
-        if not chains:
+        with (blocks if blocks is not None else contextlib.nullcontext()):
             for k in range(count):
                 one_step(k)
-            return
-        cur = torch.cuda.current_stream(dev)
-        for s, f in zip(streams, chains):
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                for k in range(count):
-                    f(k)
-        for s in streams:
-            cur.wait_stream(s)
 
     issue(warmup)
     _barrier(world)
@@ -394,9 +385,9 @@ def timed_launches(dev, world, one_step, steps, warmup, graph=True, clocks=False
 def rov6_leg(dev, rank, world, n, mode="rpm", dtype="f32", n_sub=N_SUB, steps=50, warmup=5, env_id0=None, max_steps=MAX_STEPS,
              fast=0, stats=True, graph=True, clocks=False, keep=False, groups=1):
     """One timed leg of the fused 6DoF step: n environments on this rank; returns rate per GPU (n / max-over-ranks time).
-    groups > 1: the environments are stepped as `groups` independent blocks (mvrl_rov6_step_range), each block a chain of
-    launches on its own stream - the analogue of the reference's SubprocVecEnv workers, which step their environments
-    without waiting for each other (legacy/script_0_checkScaling.py:23-40).  Every environment still takes exactly
+    groups > 1 (0 = pick the fastest of 1 / 2 / 4 / 8 by a short calibration run): the environments are stepped as
+    `groups` independent blocks (vec_tools.EnvBlocks -> mvrl_rov6_step_range), each block a chain of launches on its own
+    stream - the analogue of the reference's SubprocVecEnv workers, which step their environments without waiting for each other (legacy/script_0_checkScaling.py:23-40).  Every environment still takes exactly
     `steps` steps; a block's prologue / epilogue then overlaps the other blocks' RK4 loops instead of idling the SMs."""
     import torch
     from marinevehiclereinforcementlearning_b200 import BlueROV2Heavy6DoFVecEnv
@@ -415,23 +406,31 @@ def rov6_leg(dev, rank, world, n, mode="rpm", dtype="f32", n_sub=N_SUB, steps=50
     def one_step(k):
         env._bufs.action = acts[k % n_act].data_ptr()
         env.step_async()
-    chains = None
-    if groups > 1:
-        per = -(-n // groups)
-        per += per % 2                         # blocks start on an even environment (two environments per thread)
-        blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)]
+    from marinevehiclereinforcementlearning_b200.vec_tools import EnvBlocks
 
-        def chain(first, count):
-            def f(k):
-                env._bufs.action = acts[k % n_act].data_ptr()
-                env.step_range_async(first, count)
-            return f
-        chains = [chain(lo, cnt) for lo, cnt in blocks]
-    ms, clk = timed_launches(dev, world, one_step, steps, warmup, graph=graph, clocks=clocks, chains=chains)
+    def blocked(g):
+        if g <= 1:
+            return None, one_step
+        eb = EnvBlocks(env, g)
+
+        def blocked_step(k):
+            env._bufs.action = acts[k % n_act].data_ptr()
+            eb.step_async()
+        return eb, blocked_step
+    tried = None
+    if groups == 0:   # auto: a short calibration run of each candidate (same kernels, same environments), the fastest is timed
+        tried = {}
+        for g in ((1, 2, 4, 8) if n >= 65536 else (1,)):
+            eb, f = blocked(g)
+            tried[g] = timed_launches(dev, world, f, min(steps, 40), 3, graph=graph, blocks=eb)[0] / min(steps, 40)
+        groups = min(tried, key=tried.get)   # the times are maxima over the ranks: every rank makes the same choice
+    blocks, step_fn = blocked(groups)
+    ms, clk = timed_launches(dev, world, step_fn, steps, warmup, graph=graph, clocks=clocks, blocks=blocks)
     w = 8 if dtype == "f64" else 4
     touched = n * bytes_per_env_step(mode, w) + n_act * na * env.ld * w
     out = {"envs_per_gpu": n, "action_mode": mode, "dtype": dtype, "n_sub": n_sub, "steps": steps, "ms_per_step": ms / steps,
-           "rate_per_gpu": n / (ms / steps * 1e-3), "stream_groups": len(chains) if chains else 1,
+           "rate_per_gpu": n / (ms / steps * 1e-3), "stream_groups": len(blocks) if blocks is not None else 1,
+           "stream_groups_tried_ms_per_step": tried,
            "l2": "larger than L2" if touched > 126e6 else "working set %.0f MB is L2-resident (what stepping a shard of this size is)" % (touched / 1e6)}
     if clk is not None:
         out["clocks"] = clk
@@ -448,7 +447,7 @@ def leg_summary(leg, fp_peak):
     flop = flop_per_env_step(leg["action_mode"], leg["n_sub"])
     return {"value": leg["rate_per_gpu"], "unit": UNIT + " per GPU", "ms_per_step": leg["ms_per_step"], "envs_per_gpu": leg["envs_per_gpu"],
             "steps": leg["steps"], "algorithmic_flop_per_env_step": flop, "frac_of_fp_peak": leg["rate_per_gpu"] * flop / 1e12 / fp_peak,
-            "l2": leg["l2"]}
+            "stream_groups": leg["stream_groups"], "stream_groups_tried_ms_per_step": leg["stream_groups_tried_ms_per_step"], "l2": leg["l2"]}
 
 
 def auv_leg(dev, rank, world, n=262144, steps=50, warmup=5, field="modes", graph=True, clocks=False):
@@ -548,26 +547,24 @@ def rollout_leg(dev, rank, world, n=131072, T=128, rollouts=2, n_sub=N_SUB, cloc
 
         # groups > 1: the environments are split into independent blocks, each block a chain (actor, env step) x T on its
         # own stream - one block's actor (tensor core / XU pipe) runs beside another block's env step (FMA pipe)
-        per = -(-n // max(1, groups))
-        per += (-per) % 128                                     # whole actor tiles
-        blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)] if groups > 1 else [(0, n)]
-        streams = [torch.cuda.Stream(device=dev) for _ in blocks] if groups > 1 else []
+        eb = None
+        if groups > 1:
+            from marinevehiclereinforcementlearning_b200.vec_tools import EnvBlocks
+            eb = EnvBlocks(env, groups, align=128)           # whole actor tiles
+        blocks = eb.blocks if eb is not None else [(0, n)]
 
         def rollout():
-            if groups <= 1:
+            if eb is None:
                 for t in range(T):
                     policy_step(t)
                     env_step(t)
             else:
-                cur = torch.cuda.current_stream(dev)
-                for s, (lo, cnt) in zip(streams, blocks):
-                    s.wait_stream(cur)
-                    with torch.cuda.stream(s):
-                        for t in range(T):
-                            policy_step(t, lo, cnt)
-                            env_step(t, lo, cnt)
-                for s in streams:
-                    cur.wait_stream(s)
+                with eb:
+                    for lo, cnt, s in eb:
+                        with torch.cuda.stream(s):
+                            for t in range(T):
+                                policy_step(t, lo, cnt)
+                                env_step(t, lo, cnt)
             buf_obs[0].copy_(buf_obs[T])   # the next rollout starts where this one ended
         launches_per_step = 2 * len(blocks)
     else:
@@ -660,7 +657,7 @@ def run_ours(args, rank, local_rank, world):
     w = 8 if args.dtype == "f64" else 4
     na = ACTION_DIM[mode]
     leg = rov6_leg(dev, rank, world, n, mode, args.dtype, n_sub, args.steps, args.warmup, env_id0=id0, max_steps=args.max_steps,
-                   fast=args.fast_math, stats=not args.no_stats, graph=bool(args.graph), clocks=True, keep=True, groups=max(1, args.stream_groups))
+                   fast=args.fast_math, stats=not args.no_stats, graph=bool(args.graph), clocks=True, keep=True, groups=max(0, args.stream_groups))
     env, acts = leg["env"], leg["acts"]
     ms_per_step = leg["ms_per_step"]
     n_total = ENVS_TOTAL_STRONG if strong else world * n
@@ -700,15 +697,16 @@ def run_ours(args, rank, local_rank, world):
         xs, xw = args.extra_steps, 5
         if world > 1 and not strong:   # config 3 as written: 1 Mi environments IN TOTAL
             lo, hi = shard_range(ENVS_TOTAL_STRONG, rank, world)
-            sl = rov6_leg(dev, rank, world, hi - lo, mode, args.dtype, n_sub, max(xs, 200), xw, env_id0=lo, stats=False)
+            sl = rov6_leg(dev, rank, world, hi - lo, mode, args.dtype, n_sub, max(xs, 200), xw, env_id0=lo, stats=False, groups=max(0, args.stream_groups))
             sv = ENVS_TOTAL_STRONG / (sl["ms_per_step"] * 1e-3)
             strong_leg = {"value": sv, "unit": UNIT, "envs_total": ENVS_TOTAL_STRONG, "envs_per_gpu": hi - lo, "ms_per_step": sl["ms_per_step"],
+                          "stream_groups": sl["stream_groups"], "stream_groups_tried_ms_per_step": sl["stream_groups_tried_ms_per_step"],
                           "steps": sl["steps"], "efficiency_vs_one_gpu_with_all_envs": sv / (value / world) / world,
                           "note": "one GPU stepping all 1 Mi environments = the per-GPU rate of the weak headline (value / n_gpus)", "l2": sl["l2"]}
         if world == 1 and (mode, args.dtype, n_sub, n) == ("rpm", "f32", N_SUB, ENVS_PER_GPU):
             big = ENVS_PER_GPU
-            extra["setpoint_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "setpoint", "f32", N_SUB, xs, xw, stats=False), fp32_peak)
-            extra["force_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "force", "f32", N_SUB, xs, xw, stats=False), fp32_peak)
+            extra["setpoint_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "setpoint", "f32", N_SUB, xs, xw, stats=False, groups=0), fp32_peak)
+            extra["force_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "force", "f32", N_SUB, xs, xw, stats=False, groups=0), fp32_peak)
             extra["rpm_f64"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f64", N_SUB, xs, xw, stats=False), fp64_peak)
             extra["setpoint_f64"] = leg_summary(rov6_leg(dev, rank, world, big // 4, "setpoint", "f64", N_SUB, max(10, xs // 4), 3, stats=False), fp64_peak)
             extra["rpm_f32_nsub1"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f32", 1, xs, xw, stats=False), fp32_peak)
@@ -716,8 +714,10 @@ def run_ours(args, rank, local_rank, world):
             extra["config2_4096_envs_f64_rpm"] = leg_summary(rov6_leg(dev, rank, world, 4096, "rpm", "f64", N_SUB, 4 * xs, xw, stats=False), fp64_peak)
             extra["single_gpu_shards_rpm_f32"] = {}
             for div in (2, 4, 8, 16):
-                sl = rov6_leg(dev, rank, world, big // div, "rpm", "f32", N_SUB, 4 * xs, xw, stats=False)
+                sl = rov6_leg(dev, rank, world, big // div, "rpm", "f32", N_SUB, 4 * xs, xw, stats=False, groups=0)
                 extra["single_gpu_shards_rpm_f32"][str(big // div)] = {"value": sl["rate_per_gpu"], "ms_per_step": sl["ms_per_step"],
+                                                                       "stream_groups": sl["stream_groups"],
+                                                                       "stream_groups_tried_ms_per_step": sl["stream_groups_tried_ms_per_step"],
                                                                        "relative_to_1Mi_launch": sl["rate_per_gpu"] / (value / world), "l2": sl["l2"]}
             extra["config4_auv_262144_envs"] = auv_leg(dev, rank, world, 262144, 4 * xs, xw)
             extra["rov3_setpoint_f32"] = rov3_leg(dev, rank, world, big, "setpoint", steps=xs, warmup=xw)
@@ -725,6 +725,8 @@ def run_ours(args, rank, local_rank, world):
         extra["config5_rollout"] = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="fused")
         tl = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="torch")
         extra["config5_rollout"]["pytorch_policy_baseline"] = {k: tl[k] for k in ("value", "ms_per_step", "env_share", "policy_and_bookkeeping_us_per_step", "policy")}
+        r2g = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="fused", groups=2)
+        extra["config5_rollout"]["two_stream_groups"] = {k: r2g[k] for k in ("value", "ms_per_step", "launches_per_step", "stream_groups")}
         if world > 1:
             extra["config5_rollout"]["value_all_gpus"] = extra["config5_rollout"]["value"] * world
 
@@ -774,7 +776,10 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(n, mode, args.dtype, n_sub), "envs_per_gpu": n, "envs_total": n_total, "n_sub": n_sub,
-                           "action_mode": mode, "fast_math": bool(args.fast_math), "cuda_graph": bool(args.graph), "stream_groups": leg["stream_groups"],
+                           "action_mode": mode, "fast_math": bool(args.fast_math), "cuda_graph": bool(args.graph),
+                           # independent blocks of environments as chains of launches on their own streams (vec_tools.EnvBlocks): every
+                           # environment takes exactly `steps` steps in the timed region, a block's k-th step waits for its own (k-1)-th only
+                           "stream_groups": leg["stream_groups"], "stream_groups_tried_ms_per_step": leg["stream_groups_tried_ms_per_step"],
                            "two_envs_per_thread_ffma2": os.environ.get("MVRL_NO_X2", "0") != "1" and args.dtype == "f32", "parallelism": "env-sharded x%d, no collective on the step path" % world,
                            "l2": leg["l2"] + " (+ 4 rotating action batches)"},
                 "roofline": roofline, "cpu_baseline": cpu,
@@ -783,6 +788,9 @@ def run_ours(args, rank, local_rank, world):
                         "path": "BlueROV2Heavy6DoFVecEnv.step_host (mvrl_rov6_step_host): pinned host [N,8] actions -> pinned host obs/reward/done, "
                                 "chunked H2D / transpose / fused step / transpose / D2H pipeline (obs by copy engine, done stored into the pinned host array by the transpose kernel; the always-zero reward does not travel)"},
                 "gpu_launches": args.steps * leg["stream_groups"], "clocks": leg.get("clocks"), "episode_stats": leg.get("episode_stats")}
+        tried = leg["stream_groups_tried_ms_per_step"]
+        if tried and 1 in tried:   # the same workload with ONE launch per step (stream_groups = 1), from the calibration run
+            line["single_launch_per_step"] = {"value": n_total / (tried[1] * 1e-3), "unit": UNIT, "ms_per_step": tried[1], "steps": min(args.steps, 40)}
         if strong_leg is not None:
             line["strong"] = strong_leg
         if extra:
@@ -814,7 +822,7 @@ def run_secondary(args, rank, local_rank, world):
     else:
         n = args.envs if args.envs != ENVS_PER_GPU else 131072
         rollouts = max(2, args.steps // args.rollout_len)
-        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True, policy=args.policy, groups=args.stream_groups)
+        r = rollout_leg(dev, rank, world, n, args.rollout_len, rollouts, args.n_sub, clocks=True, policy=args.policy, groups=max(1, args.stream_groups))
         metric, dtype = "6DoF rollout collection env-steps/sec (policy included)", "f32 env; policy bf16 operands / fp32 accumulate (fused) or TF32 (torch)"
         cfg = {"workload": "rollout: 6DoF set-point env + MLP 9-128-128-128-6 GELU Gaussian policy, %d envs/GPU, %d-step rollouts, "
                            "nSub=%d, CUDA-graph replay, stats all-reduce per rollout" % (n, args.rollout_len, args.n_sub)}
@@ -855,8 +863,9 @@ def main():
     ap.add_argument("--max-steps", type=int, default=MAX_STEPS, help="episode length (diagnostics; default = the reference's 250)")
     ap.add_argument("--graph", type=int, default=1, help="1: the K timed launches are replayed as one CUDA graph; 0: K separate launches")
     ap.add_argument("--bind-numa", type=int, default=1, help="1: bind each rank to the CPUs of its GPU's NUMA node (host buffers of the e2e leg)")
-    ap.add_argument("--stream-groups", type=int, default=1,
-                    help="step the environments of a rank as this many independent blocks, each a chain of launches on its own stream (default 1: one launch per step)")
+    ap.add_argument("--stream-groups", type=int, default=0,
+                    help="step the environments of a rank as this many independent blocks, each a chain of launches on its own stream "
+                         "(vec_tools.EnvBlocks); 1 = one launch per step; 0 (default) = rov6: the fastest of 1 / 2 / 4 / 8 by a short calibration run, rollout: 1")
     ap.add_argument("--no-stats", action="store_true", help="diagnostics: do not accumulate episode statistics in the step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

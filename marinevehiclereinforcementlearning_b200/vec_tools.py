@@ -8,7 +8,10 @@
 * ``Sb3VecEnv`` - numpy-facing adapter with the Stable-Baselines3 ``VecEnv`` protocol the legacy training
   scripts drive (tag_00.../main_00_sbl.py:145-146), including ``VecMonitor``'s ``r,l,t`` CSV;
 * ``SymmetryReplayBuffer`` - the mirror-image augmenting replay buffer of
-  tag_00.../main_02_sbl_contrib_customBuffer.py:57-160, filled on the device by ``mvrl_replay_add_symmetric``.
+  tag_00.../main_02_sbl_contrib_customBuffer.py:57-160, filled on the device by ``mvrl_replay_add_symmetric``;
+* ``EnvBlocks`` - a batched env stepped as independent blocks of environments, each block a chain of launches on its own
+  stream: what the ``SubprocVecEnv`` workers of the legacy scripts are to each other (tag_00.../main_00_sbl.py:145-146,
+  script_0_checkScaling.py:23-40).
 """
 import csv
 import json
@@ -38,6 +41,78 @@ def _env_kind(env):
     if "Auv" in name:
         return "auv"
     raise TypeError("unsupported env type %s" % name)
+
+
+class EnvBlocks:
+    """Step a batched 6DoF env as ``groups`` independent blocks of environments, block ``g`` on its own CUDA stream.
+
+    The reference scales by running ``nProc`` workers that step their environments without waiting for each other
+    (``SubprocVecEnv([make_env(i) for i in range(nProc)])``, tag_00.../main_00_sbl.py:145-146; its scaling check,
+    script_0_checkScaling.py:23-40, times exactly that).  On the GPU the same independence pays differently: one launch
+    per step leaves the SMs under-used while its first CTAs load and its last ones store (a 131 072-environment step is
+    1.15 waves of CTAs: 30.2 us), whereas chains of smaller launches on separate streams drift out of phase, so one
+    block's prologue / epilogue runs under the other blocks' RK4 loops (four blocks: 22.8 us, the rate of a 1 Mi-env
+    launch; profiles/r2_zz_stream_groups.jsonl).  Results do not depend on the blocking: every block runs the same kernel on
+    its own environments (``mvrl_rov6_step_range``), random draws are keyed on the global environment id.
+
+        blocks = EnvBlocks(env, 4)
+        with blocks:                       # fork: the block streams wait for the caller's stream
+            for k in range(K):
+                blocks.step_async()        # block g's k-th step queues behind its own (k-1)-th only
+        # join: the caller's stream waits for every block - env.obs / env.systemState are complete from here on
+
+    ``for lo, cnt, stream in blocks:`` gives the caller the blocks to queue its own per-block work (a policy) on.
+    Works eagerly and inside CUDA-graph capture (the block streams fork from and re-join the capturing stream).
+    ``align``: block starts are multiples of it (2 keeps the two-environments-per-thread kernel's 8-byte row alignment;
+    128 = the rollout actor's tile)."""
+
+    def __init__(self, env, groups, align=2):
+        if not hasattr(env, "step_range_async"):
+            raise TypeError("EnvBlocks needs a batched env with step_range_async (the 6DoF VecEnv)")
+        groups, align = int(groups), int(align)
+        if groups < 1 or align < 1:
+            raise ValueError("groups and align must be positive")
+        self.env = env
+        n = env.num_envs
+        per = -(-n // groups)
+        per += (-per) % align
+        self.blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)]
+        self.streams = [torch.cuda.Stream(device=env.device) for _ in self.blocks]
+        self._forked = False
+
+    def __len__(self):
+        return len(self.blocks)
+
+    def __iter__(self):
+        return iter([(lo, cnt, s) for (lo, cnt), s in zip(self.blocks, self.streams)])
+
+    def fork(self):
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        self._forked = True
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+        self._forked = False
+
+    def __enter__(self):
+        self.fork()
+        return self
+
+    def __exit__(self, *exc):
+        self.join()
+        return False
+
+    def step_async(self):
+        """Queue one env step of every block on its stream (actions are read from the env's action buffer)."""
+        if not self._forked:
+            raise RuntimeError("EnvBlocks.step_async outside fork() / join() (use `with blocks:`)")
+        for (lo, cnt), s in zip(self.blocks, self.streams):
+            with torch.cuda.stream(s):
+                self.env.step_range_async(lo, cnt)
 
 
 class TrajectoryRecorder:

@@ -148,3 +148,48 @@ def test_symmetry_replay_buffer_vs_oracle_larger_batch():
         assert np.array_equal(getattr(buf, name).cpu().numpy().astype(np.float64), getattr(ref, name)), name
     s = buf.sample(256)
     assert s["observations"].shape == (256, 11) and s["actions"].shape == (256, 3) and s["dones"].dtype == torch.uint8
+
+
+@pytest.mark.parametrize("mode,groups,n", [("rpm", 3, 10007), ("setpoint", 4, 4096), ("force", 2, 130)])
+def test_env_blocks_on_their_own_streams_match_whole_batch_launches_bitwise(mode, groups, n):
+    """EnvBlocks (independent blocks of environments, each a chain of launches on its own stream - the SubprocVecEnv workers
+    of tag_00.../main_00_sbl.py:145-146 on the device) against one launch per step: same kernels, random draws keyed on the
+    global environment id, so state / observation / done / episode counters / statistics agree bit for bit - eagerly and
+    as parallel branches of one captured CUDA graph; auto-reset fires several times (maxSteps = 4)."""
+    na = 8 if mode == "rpm" else 6
+    scale = {"rpm": 3500.0, "force": 40.0, "setpoint": 1.0}[mode]
+    K = 11
+    g = torch.Generator(device=DEV).manual_seed(5)
+    envs = [BlueROV2Heavy6DoFVecEnv(n, action_mode=mode, dtype=torch.float32, device=DEV, maxSteps=4, auto_reset=True, seed=3) for _ in range(3)]
+    acts = [(torch.rand((na, envs[0].ld), generator=g, device=DEV) * 2 - 1) * scale for _ in range(3)]
+    for e in envs:
+        e.reset()
+    whole, eager, graphed = envs
+    for k in range(K):
+        whole._bufs.action = acts[k % 3].data_ptr()
+        whole.step_async()
+    blocks = vec_tools.EnvBlocks(eager, groups)
+    assert len(blocks) == groups and sum(c for _, c in blocks.blocks) == n and all(lo % 2 == 0 for lo, _ in blocks.blocks)
+    with pytest.raises(RuntimeError):
+        blocks.step_async()                     # outside fork() / join()
+    with blocks:
+        for k in range(K):
+            eager._bufs.action = acts[k % 3].data_ptr()
+            blocks.step_async()
+    gb = vec_tools.EnvBlocks(graphed, groups)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            with gb:
+                for k in range(K):
+                    graphed._bufs.action = acts[k % 3].data_ptr()
+                    gb.step_async()
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    for e in (eager, graphed):
+        assert torch.equal(e.systemState, whole.systemState) and torch.equal(e._obs, whole._obs)
+        assert torch.equal(e._done, whole._done) and torch.equal(e._istep, whole._istep) and torch.equal(e._episode, whole._episode)
+        assert e.episode_stats() == whole.episode_stats()
