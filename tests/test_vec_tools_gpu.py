@@ -189,7 +189,9 @@ def test_env_blocks_on_their_own_streams_match_whole_batch_launches_bitwise(mode
     torch.cuda.current_stream().wait_stream(side)
     graph.replay()
     torch.cuda.synchronize()
+    stats = whole.episode_stats()               # (reading resets the accumulators)
+    assert stats["episodes"] == 2 * n           # 11 steps with maxSteps = 4: every environment finished two episodes
     for e in (eager, graphed):
         assert torch.equal(e.systemState, whole.systemState) and torch.equal(e._obs, whole._obs)
         assert torch.equal(e._done, whole._done) and torch.equal(e._istep, whole._istep) and torch.equal(e._episode, whole._episode)
-        assert e.episode_stats() == whole.episode_stats()
+        assert e.episode_stats() == stats
