@@ -450,32 +450,74 @@ def leg_summary(leg, fp_peak):
             "stream_groups": leg["stream_groups"], "stream_groups_tried_ms_per_step": leg["stream_groups_tried_ms_per_step"], "l2": leg["l2"]}
 
 
-def auv_leg(dev, rank, world, n=262144, steps=50, warmup=5, field="modes", graph=True, clocks=False):
+def merge_episode_stats(stats):
+    """Episode statistics of several shards as one (sums, weighted means, extremes)."""
+    if len(stats) == 1:
+        return stats[0]
+    ep = sum(st["episodes"] for st in stats)
+    out = {"episodes": ep, "nonfinite": sum(st.get("nonfinite", 0) for st in stats)}
+    for k in ("mean_length", "mean_return"):
+        out[k] = (sum(st[k] * st["episodes"] for st in stats if st["episodes"]) / ep) if ep else float("nan")
+    live = [st for st in stats if st["episodes"]]
+    out["min_return"] = min(st["min_return"] for st in live) if live else float("nan")
+    out["max_return"] = max(st["max_return"] for st in live) if live else float("nan")
+    return out
+
+
+def auv_leg(dev, rank, world, n=262144, steps=50, warmup=5, field="modes", graph=True, clocks=False, groups=1):
     """Config 4: legacy AuvEnv, fp32, synthetic turbulence field [2000, 41, 61] scaled like verySimpleAuv.py:104,
-    a ~ U(-1, 1)^3, noiseMag* = 0.1.  One step = one auv_step launch over the batch."""
+    a ~ U(-1, 1)^3, noiseMag* = 0.1.  One step = one auv_step launch over the batch - or, groups > 1 (0 = the fastest of
+    1 / 2 / 4 by a short calibration run), one launch per shard: the batch as `groups` env objects with consecutive env_id0,
+    each stepping as a chain on its own stream (vec_tools.EnvShards; the reference's SubprocVecEnv workers)."""
     import torch
     from marinevehiclereinforcementlearning_b200 import AuvVecEnv
     from marinevehiclereinforcementlearning_b200.tag_00_Dec2023_simpleControlTurbulence import flowGenerator
+    from marinevehiclereinforcementlearning_b200.vec_tools import EnvShards
     ltm = np.load(os.path.join(ROOT, "tests", "golden", "golden_legacy.npz"))["ltm"]   # the reference's ltm.npy (41 x 61 x 3)
     flow = flowGenerator.ReconstructedFlow.synthetic(lt_mean=ltm, nt=2000, seed=7, sigma=0.05, kind=field, dtype=torch.float32, device=dev)
     flow.scale(11., 1.0, 2.0, translate=(-1.65, -1.1))
-    env = AuvVecEnv(n, flow, seed=1234, env_id0=rank * n, noiseMagCoeffs=0.1, noiseMagActuation=0.1, auto_reset=True,
-                    dtype=torch.float32, record_terminal_obs=False)
-    env.reset()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = [torch.rand((3, env.ld), generator=gen, device=dev) * 2 - 1 for _ in range(8)]
 
-    def one_step(k):
-        env._bufs.action = acts[k % 8].data_ptr()
-        env.step_async()
-    ms, clk = timed_launches(dev, world, one_step, steps, warmup, graph=graph, clocks=clocks)
+    def make(g):
+        per = -(-n // g)
+        envs, fns = [], []
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        for lo in range(0, n, per):
+            e = AuvVecEnv(min(per, n - lo), flow, seed=1234, env_id0=rank * n + lo, noiseMagCoeffs=0.1, noiseMagActuation=0.1, auto_reset=True,
+                          dtype=torch.float32, record_terminal_obs=False)
+            e.reset()
+            acts = [torch.rand((3, e.ld), generator=gen, device=dev) * 2 - 1 for _ in range(8)]
+            envs.append(e)
+            fns.append(acts)
+        if g == 1:
+            def one_step(k):
+                envs[0]._bufs.action = fns[0][k % 8].data_ptr()
+                envs[0].step_async()
+            return envs, None, one_step
+        shards = EnvShards(envs)
+
+        def sharded_step(k):
+            for e, acts in zip(envs, fns):
+                e._bufs.action = acts[k % 8].data_ptr()
+            shards.step_async()
+        return envs, shards, sharded_step
+    tried = None
+    if groups == 0:
+        tried = {}
+        for g in (1, 2, 4):
+            _, sh, f = make(g)
+            tried[g] = timed_launches(dev, world, f, min(steps, 40), 5, graph=graph, blocks=sh)[0] / min(steps, 40)
+        groups = min(tried, key=tried.get)
+    envs, shards, step_fn = make(groups)
+    ms, clk = timed_launches(dev, world, step_fn, steps, warmup, graph=graph, clocks=clocks, blocks=shards)
     rate = n / (ms / steps * 1e-3)
     # state 6 r/w, action 3 r, obs 11 w, reward w, mults 11 r, target 2 r, err_o 3 r/w, ring 30 r + 3 w, return r/w, done 1, istep 8
     nbytes = (12 + 3 + 11 + 1 + 11 + 2 + 6 + 33 + 2) * 4 + 9
     peaks, peak_src = measured_peaks()
     return {"value": rate, "unit": UNIT + " per GPU", "ms_per_step": ms / steps, "envs_per_gpu": n, "steps": steps, "field": field,
+            "stream_groups": len(envs), "stream_groups_tried_ms_per_step": tried,
             "hbm_gbs": rate * nbytes / 1e9, "frac_of_hbm_peak": rate * nbytes / 1e9 / peaks["hbm_gbs"], "bytes_per_env_step": nbytes,
-            "gathered_bytes_per_env_step_from_l2": 64, "peak_source": peak_src, "clocks": clk, "episode_stats": env.episode_stats(),
+            "gathered_bytes_per_env_step_from_l2": 64, "peak_source": peak_src, "clocks": clk,
+            "episode_stats": merge_episode_stats([e.episode_stats() for e in envs]),
             "l2": "40 MB field is L2-resident by design; per-env arrays (87 MB / step) rotate through 8 action batches"}
 
 
@@ -804,14 +846,14 @@ def run_secondary(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if args.workload == "auv":
         n = args.envs if args.envs != ENVS_PER_GPU else 262144
-        r = auv_leg(dev, rank, world, n, args.steps, args.warmup, field=args.field, graph=bool(args.graph), clocks=True)
+        r = auv_leg(dev, rank, world, n, args.steps, args.warmup, field=args.field, graph=bool(args.graph), clocks=True, groups=max(0, args.stream_groups))
         metric, dtype = "legacy AuvEnv env-steps/sec", "f32"
         cfg = {"workload": "auv_step fp32: legacy verySimpleAuv, %d envs/GPU, field [2000,41,61,2] (%s), a~U(-1,1)^3" % (n, args.field),
-               "cuda_graph": bool(args.graph), "smem_staged_gather": os.environ.get("MVRL_AUV_NO_STAGE", "0") != "1", "l2": r["l2"]}
+               "cuda_graph": bool(args.graph), "stream_groups": r["stream_groups"], "stream_groups_tried_ms_per_step": r["stream_groups_tried_ms_per_step"], "smem_staged_gather": os.environ.get("MVRL_AUV_NO_STAGE", "0") != "1", "l2": r["l2"]}
         extra = {"roofline": {"bound": "hbm", "achieved": r["hbm_gbs"], "peak": r["hbm_gbs"] / r["frac_of_hbm_peak"], "unit": "GB/s",
                               "frac": r["frac_of_hbm_peak"], "traffic": None, "bytes_per_env_step": r["bytes_per_env_step"],
                               "gathered_bytes_per_env_step_from_l2": 64, "peak_source": r["peak_source"]}}
-        launches = args.steps
+        launches = args.steps * r["stream_groups"]
     elif args.workload == "rov3":
         mode = "rpm" if args.action_mode == "rpm" else "setpoint"
         r = rov3_leg(dev, rank, world, args.envs, mode, args.n_sub, args.steps, args.warmup, clocks=True)

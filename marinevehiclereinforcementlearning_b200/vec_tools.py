@@ -11,7 +11,7 @@
   tag_00.../main_02_sbl_contrib_customBuffer.py:57-160, filled on the device by ``mvrl_replay_add_symmetric``;
 * ``EnvBlocks`` - a batched env stepped as independent blocks of environments, each block a chain of launches on its own
   stream: what the ``SubprocVecEnv`` workers of the legacy scripts are to each other (tag_00.../main_00_sbl.py:145-146,
-  script_0_checkScaling.py:23-40).
+  script_0_checkScaling.py:23-40); ``EnvShards`` - the same for separate env objects of any kind.
 """
 import csv
 import json
@@ -68,7 +68,7 @@ class EnvBlocks:
 
     def __init__(self, env, groups, align=2):
         if not hasattr(env, "step_range_async"):
-            raise TypeError("EnvBlocks needs a batched env with step_range_async (the 6DoF VecEnv)")
+            raise TypeError("EnvBlocks needs a batched env with step_range_async (the 6DoF VecEnv); use EnvShards for separate env objects")
         groups, align = int(groups), int(align)
         if groups < 1 or align < 1:
             raise ValueError("groups and align must be positive")
@@ -77,23 +77,27 @@ class EnvBlocks:
         per = -(-n // groups)
         per += (-per) % align
         self.blocks = [(lo, min(per, n - lo)) for lo in range(0, n, per)]
-        self.streams = [torch.cuda.Stream(device=env.device) for _ in self.blocks]
+        self._init_streams(env.device, len(self.blocks))
+
+    def _init_streams(self, device, count):
+        self.device = device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(count)]
         self._forked = False
 
     def __len__(self):
-        return len(self.blocks)
+        return len(self.streams)
 
     def __iter__(self):
         return iter([(lo, cnt, s) for (lo, cnt), s in zip(self.blocks, self.streams)])
 
     def fork(self):
-        cur = torch.cuda.current_stream(self.env.device)
+        cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(cur)
         self._forked = True
 
     def join(self):
-        cur = torch.cuda.current_stream(self.env.device)
+        cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             cur.wait_stream(s)
         self._forked = False
@@ -106,13 +110,39 @@ class EnvBlocks:
         self.join()
         return False
 
+    def _require_fork(self):
+        if not self._forked:
+            raise RuntimeError("%s.step_async outside fork() / join() (use `with blocks:`)" % type(self).__name__)
+
     def step_async(self):
         """Queue one env step of every block on its stream (actions are read from the env's action buffer)."""
-        if not self._forked:
-            raise RuntimeError("EnvBlocks.step_async outside fork() / join() (use `with blocks:`)")
+        self._require_fork()
         for (lo, cnt), s in zip(self.blocks, self.streams):
             with torch.cuda.stream(s):
                 self.env.step_range_async(lo, cnt)
+
+
+class EnvShards(EnvBlocks):
+    """The same for SEPARATE env objects of any kind (6DoF, 3DoF, legacy) - literally the reference's list of workers, each
+    with its own buffers: ``EnvShards([AuvVecEnv(n // 4, flow, env_id0=i * (n // 4), ...) for i in range(4)])``.  Shards
+    created with consecutive ``env_id0`` draw the same random numbers as one env over all of them (tested bitwise), and
+    each steps as a chain on its own stream.  ``for env, stream in shards:`` to queue per-shard work."""
+
+    def __init__(self, envs):
+        self.envs = list(envs)
+        if not self.envs:
+            raise ValueError("EnvShards needs at least one env")
+        self._init_streams(self.envs[0].device, len(self.envs))
+
+    def __iter__(self):
+        return iter(list(zip(self.envs, self.streams)))
+
+    def step_async(self):
+        """Queue one env step of every shard on its stream (each reads its own action buffer)."""
+        self._require_fork()
+        for e, s in zip(self.envs, self.streams):
+            with torch.cuda.stream(s):
+                e.step_async()
 
 
 class TrajectoryRecorder:

@@ -195,3 +195,37 @@ def test_env_blocks_on_their_own_streams_match_whole_batch_launches_bitwise(mode
         assert torch.equal(e.systemState, whole.systemState) and torch.equal(e._obs, whole._obs)
         assert torch.equal(e._done, whole._done) and torch.equal(e._istep, whole._istep) and torch.equal(e._episode, whole._episode)
         assert e.episode_stats() == stats
+
+
+def test_env_shards_on_their_own_streams_match_one_env_bitwise():
+    """EnvShards: separate env objects with consecutive env_id0 (the reference's list of SubprocVecEnv workers), each a chain of
+    launches on its own stream, against one env over all environments - legacy env, fp32, noise and auto-reset on."""
+    g = load_golden("legacy")
+    flow = make_flow(g, torch.float32)
+    n, K = 3000, 12
+    kw = dict(noiseMagCoeffs=0.1, noiseMagActuation=0.1, maxSteps=5, auto_reset=True, seed=9, dtype=torch.float32)
+    whole = AuvVecEnv(n, flow, **kw)
+    parts = [AuvVecEnv(n // 3, flow, env_id0=i * (n // 3), **kw) for i in range(3)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    acts = [torch.rand((n, 3), generator=gen, device=DEV) * 2 - 1 for _ in range(K)]
+    for k in range(K):
+        whole.step_async(acts[k])
+    shards = vec_tools.EnvShards(parts)
+    assert len(shards) == 3
+    with pytest.raises(RuntimeError):
+        shards.step_async()
+    for k in range(K):                         # the actions go in on the caller's stream, before the fork
+        for i, p in enumerate(parts):
+            p.set_actions(acts[k][i * (n // 3):(i + 1) * (n // 3)])
+        with shards:
+            shards.step_async()
+    torch.cuda.synchronize()
+    m = n // 3
+    for i, p in enumerate(parts):
+        assert torch.equal(p._obs[:, :m], whole._obs[:, i * m:(i + 1) * m]) and torch.equal(p._state[:, :m], whole._state[:, i * m:(i + 1) * m])
+        assert torch.equal(p._done[:m], whole._done[i * m:(i + 1) * m]) and torch.equal(p._reward[:m], whole._reward[i * m:(i + 1) * m])
+    episodes = whole.episode_stats()["episodes"]
+    assert sum(p.episode_stats()["episodes"] for p in parts) == episodes and episodes >= 2 * n   # maxSteps = 5, 12 steps (+ bounds terminations)
