@@ -467,7 +467,7 @@ def merge_episode_stats(stats):
 def auv_leg(dev, rank, world, n=262144, steps=50, warmup=5, field="modes", graph=True, clocks=False, groups=1):
     """Config 4: legacy AuvEnv, fp32, synthetic turbulence field [2000, 41, 61] scaled like verySimpleAuv.py:104,
     a ~ U(-1, 1)^3, noiseMag* = 0.1.  One step = one auv_step launch over the batch - or, groups > 1 (0 = the fastest of
-    1 / 2 / 4 by a short calibration run), one launch per shard: the batch as `groups` env objects with consecutive env_id0,
+    1 / 2 / 4 / 8 by a short calibration run), one launch per shard: the batch as `groups` env objects with consecutive env_id0,
     each stepping as a chain on its own stream (vec_tools.EnvShards; the reference's SubprocVecEnv workers)."""
     import torch
     from marinevehiclereinforcementlearning_b200 import AuvVecEnv
@@ -503,7 +503,7 @@ def auv_leg(dev, rank, world, n=262144, steps=50, warmup=5, field="modes", graph
     tried = None
     if groups == 0:
         tried = {}
-        for g in (1, 2, 4):
+        for g in (1, 2, 4, 8):
             _, sh, f = make(g)
             tried[g] = timed_launches(dev, world, f, min(steps, 40), 5, graph=graph, blocks=sh)[0] / min(steps, 40)
         groups = min(tried, key=tried.get)
@@ -761,7 +761,7 @@ def run_ours(args, rank, local_rank, world):
                                                                        "stream_groups": sl["stream_groups"],
                                                                        "stream_groups_tried_ms_per_step": sl["stream_groups_tried_ms_per_step"],
                                                                        "relative_to_1Mi_launch": sl["rate_per_gpu"] / (value / world), "l2": sl["l2"]}
-            extra["config4_auv_262144_envs"] = auv_leg(dev, rank, world, 262144, 4 * xs, xw)
+            extra["config4_auv_262144_envs"] = auv_leg(dev, rank, world, 262144, 4 * xs, xw, groups=0)
             extra["rov3_setpoint_f32"] = rov3_leg(dev, rank, world, big, "setpoint", steps=xs, warmup=xw)
             extra["rov3_rpm_f32"] = rov3_leg(dev, rank, world, big, "rpm", steps=xs, warmup=xw)
         extra["config5_rollout"] = rollout_leg(dev, rank, world, 131072, args.rollout_len, rollouts=2, policy="fused")
