@@ -142,3 +142,21 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_merges_shard_episode_statistics():
+    """bench.py's config-4 leg steps the batch as several env objects (vec_tools.EnvShards): their episode statistics are
+    reported as one record - sums, episode-weighted means, extremes; shards without a finished episode carry NaNs."""
+    import math
+    sys.path.insert(0, ROOT)
+    import bench
+    nan = float("nan")
+    a = {"episodes": 10, "mean_length": 5.0, "mean_return": -2.0, "min_return": -7.0, "max_return": 1.0, "nonfinite": 0}
+    b = {"episodes": 30, "mean_length": 9.0, "mean_return": 2.0, "min_return": -3.0, "max_return": 4.0, "nonfinite": 2}
+    idle = {"episodes": 0, "mean_length": nan, "mean_return": nan, "min_return": nan, "max_return": nan, "nonfinite": 0}
+    assert bench.merge_episode_stats([a]) is a
+    m = bench.merge_episode_stats([a, idle, b])
+    assert m["episodes"] == 40 and m["nonfinite"] == 2 and m["min_return"] == -7.0 and m["max_return"] == 4.0
+    assert abs(m["mean_length"] - 8.0) < 1e-12 and abs(m["mean_return"] - 1.0) < 1e-12
+    e = bench.merge_episode_stats([idle, idle])
+    assert e["episodes"] == 0 and math.isnan(e["mean_length"]) and math.isnan(e["min_return"])
