@@ -160,3 +160,95 @@ def test_bench_merges_shard_episode_statistics():
     assert abs(m["mean_length"] - 8.0) < 1e-12 and abs(m["mean_return"] - 1.0) < 1e-12
     e = bench.merge_episode_stats([idle, idle])
     assert e["episodes"] == 0 and math.isnan(e["mean_length"]) and math.isnan(e["min_return"])
+
+
+class _FakeStream:
+    """Stands in for torch.cuda.Stream on a box without a GPU: records what it was made to wait for."""
+    def __init__(self, device=None):
+        self.device, self.waited = device, []
+
+    def wait_stream(self, other):
+        self.waited.append(other)
+
+
+def _fake_cuda(monkeypatch):
+    import contextlib
+    import torch
+    cur = {"s": _FakeStream("caller")}
+
+    @contextlib.contextmanager
+    def use(s):
+        prev, cur["s"] = cur["s"], s
+        try:
+            yield
+        finally:
+            cur["s"] = prev
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: cur["s"])
+    monkeypatch.setattr(torch.cuda, "stream", use)
+    return cur
+
+
+def test_env_blocks_host_logic_with_fake_streams(monkeypatch):
+    """vec_tools.EnvBlocks / EnvShards, host side only (the CUDA part is tests/test_vec_tools_gpu.py): the blocks tile the
+    batch once, start on multiples of `align`, every block's step is queued on ITS stream, the block streams wait for the
+    caller's stream at the fork and the caller's stream waits for every block stream at the join."""
+    from marinevehiclereinforcementlearning_b200 import vec_tools
+    cur = _fake_cuda(monkeypatch)
+    caller = cur["s"]
+
+    class Env:
+        num_envs, device = 10007, "cuda:0"
+
+        def __init__(self):
+            self.calls = []
+
+        def step_range_async(self, first, count):
+            self.calls.append((first, count, cur["s"]))
+
+    for n, groups, align in [(10007, 3, 2), (131072, 8, 2), (131072, 3, 128), (130, 8, 128), (5, 1, 2), (7, 7, 1)]:
+        env = Env()
+        env.num_envs = n
+        b = vec_tools.EnvBlocks(env, groups, align)
+        assert 1 <= len(b) <= groups and len(b.streams) == len(b.blocks)
+        covered = []
+        for lo, cnt in b.blocks:
+            assert lo % align == 0 and cnt > 0
+            covered += list(range(lo, lo + cnt))
+        assert covered == list(range(n))                       # every environment once, in order
+        with pytest.raises(RuntimeError):
+            b.step_async()                                     # not forked
+        with b:
+            assert all(s.waited == [caller] for s in b.streams)
+            b.step_async()
+            b.step_async()
+        assert caller.waited[-len(b):] == b.streams            # joined
+        assert [(lo, cnt) for lo, cnt, _ in env.calls] == b.blocks * 2
+        assert [s for _, _, s in env.calls] == b.streams * 2    # block g always on stream g
+        assert [(lo, cnt, s) for lo, cnt, s in b] == [(lo, cnt, s) for (lo, cnt), s in zip(b.blocks, b.streams)]
+        with pytest.raises(RuntimeError):
+            b.step_async()                                     # joined again
+    with pytest.raises(TypeError):
+        vec_tools.EnvBlocks(object(), 2)
+    with pytest.raises(ValueError):
+        vec_tools.EnvBlocks(Env(), 0)
+
+    class Shard:
+        device = "cuda:0"
+
+        def __init__(self):
+            self.on = []
+
+        def step_async(self):
+            self.on.append(cur["s"])
+
+    parts = [Shard() for _ in range(3)]
+    sh = vec_tools.EnvShards(parts)
+    assert len(sh) == 3 and [e for e, _ in sh] == parts
+    with pytest.raises(RuntimeError):
+        sh.step_async()
+    with sh:
+        sh.step_async()
+    assert [p.on for p in parts] == [[s] for s in sh.streams] and caller.waited[-3:] == sh.streams
+    with pytest.raises(ValueError):
+        vec_tools.EnvShards([])
