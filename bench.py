@@ -8,15 +8,22 @@ Workload (config 3 of BASELINE.json): BlueROV2 Heavy 6DoF,
 fp32, 1 048 576 environments PER GPU (weak scaling: the path shards by
 environment with no data-path collective), direct thruster-rpm actions
 ~U(-3500, 3500) (seed 1234 + rank), dt = 0.2 s as nSub = 8 fixed RK4 sub-steps,
-maxSteps = 250 with auto-reset.  One "step" = one launch of the fused step
-kernel over the whole batch.  Prints ONE JSON line (rank 0).
+maxSteps = 250 with auto-reset.  One "step" = one pass of the fused step kernel
+over the whole batch: every environment advances by one env step.  The pass is
+G launches, one per block of environments (vec_tools.EnvBlocks: the blocks are
+independent, each steps as its own chain on its own stream, like the reference's
+SubprocVecEnv workers); G is the fastest of 1 / 2 / 4 / 8 in a 40-step calibration
+run unless --stream-groups fixes it, the line says which (config.stream_groups)
+and carries the one-launch-per-step figure of the same run beside the headline
+(single_launch_per_step).  Prints ONE JSON line (rank 0).
 
 Next to the headline the line carries (all measured in the same run, a few seconds in total):
   "strong"  (N > 1) the config as written - 1 048 576 environments IN TOTAL, N / G per GPU (`--scaling strong`
             makes that the headline instead);
   "extra"   short legs of the other configurations: set-point (the reference's Gym semantics) / force modes, fp64,
-            n_sub 1 and 4, config 2 (4096 envs fp64), config 4 (legacy auv_step), the 3DoF env, config 5 (rollout
-            collection with the PyTorch MLP policy, at every N, with the episode-statistics all-reduce), and at N = 1
+            n_sub 1 and 4, config 2 (4096 envs fp64), config 4 (legacy auv_step, over calibrated vec_tools.EnvShards),
+            the 3DoF env, config 5 (rollout collection: fused actor kernel + env step, at every N, with the
+            episode-statistics all-reduce; the PyTorch-policy baseline and the two-block form beside it), and at N = 1
             the single-GPU rates of the 1/2, 1/4, 1/8, 1/16 shards of the 1 Mi batch.
 
 `--impl reference` times the reference's CPU implementation of the same path:
