@@ -756,7 +756,7 @@ def run_ours(args, rank, local_rank, world):
             big = ENVS_PER_GPU
             extra["setpoint_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "setpoint", "f32", N_SUB, xs, xw, stats=False, groups=0), fp32_peak)
             extra["force_f32"] = leg_summary(rov6_leg(dev, rank, world, big, "force", "f32", N_SUB, xs, xw, stats=False, groups=0), fp32_peak)
-            extra["rpm_f64"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f64", N_SUB, xs, xw, stats=False), fp64_peak)
+            extra["rpm_f64"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f64", N_SUB, xs, xw, stats=False, groups=0), fp64_peak)
             extra["setpoint_f64"] = leg_summary(rov6_leg(dev, rank, world, big // 4, "setpoint", "f64", N_SUB, max(10, xs // 4), 3, stats=False), fp64_peak)
             extra["rpm_f32_nsub1"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f32", 1, xs, xw, stats=False), fp32_peak)
             extra["rpm_f32_nsub4"] = leg_summary(rov6_leg(dev, rank, world, big, "rpm", "f32", 4, xs, xw, stats=False), fp32_peak)
